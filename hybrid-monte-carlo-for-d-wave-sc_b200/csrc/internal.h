@@ -1,0 +1,184 @@
+// internal.h -- shared declarations of libdwhmc (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "stedc_tree.h"
+
+#define DW_NB 32          // Householder panel width (tridiagonalisation and back-transform blocks)
+#define DW_LEAF 36        // largest D&C leaf
+#define DW_NSPLIT 4       // column splits of the trailing-matrix hemv
+#define DW_FCHUNK 32      // eigenvector columns per CTA in the bond-correlator kernel
+
+typedef double2 cplx;
+
+// per-chain activity mask: chain b takes part in leapfrog step `step` iff step <= nt[b]
+// (steps are 1-based; nt == nullptr means every chain is active)
+struct Mask {
+  const int* nt;
+  int step;
+  __host__ __device__ bool on(int b) const { return nt == nullptr || step <= nt[b]; }
+};
+static inline Mask no_mask() { Mask m; m.nt = nullptr; m.step = 0; return m; }
+
+struct DcLevelDev {
+  int nmerge;
+  int max_m;
+  int* off;   // device [nmerge]
+  int* n1;
+  int* n2;
+};
+
+struct Handle {
+  int device = 0;
+  int B = 0, Lx = 0, Ly = 0, N = 0, n = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool profiling = false;
+  double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void*> allocs;    // everything cudaMalloc'ed, for destroy
+
+  // lattice (device, 0-based int32, [dir * N + site])
+  int* nn = nullptr;
+  int* nnn = nullptr;
+  // per-chain parameters, device [6*B]: t, tp, mu, beta, J, mass (each a [B] slice) + host mirror
+  double* par = nullptr;
+  std::vector<double> h_par;
+  bool params_set = false;
+  // state
+  double* w = nullptr;          // disorder [N*B]
+  cplx* delta = nullptr;        // [2N*B]
+  cplx* pi = nullptr;
+  cplx* force = nullptr;
+  cplx* delta_backup = nullptr;
+  // what cache.H_base holds in the reference: static part as of init_static_H!, pairing as of update_H_BdG!
+  double* Hs_w = nullptr;       // [N*B] disorder snapshot
+  double* Hs_par = nullptr;     // [3*B] (t, tp, mu) snapshot, slices of [B]
+  cplx* Hs_delta = nullptr;     // [2N*B]
+  bool static_set = false;
+  // eigensystems
+  double *E_cur = nullptr, *E_prop = nullptr;   // [n*B]
+  cplx *U_cur = nullptr, *U_prop = nullptr;     // [n*n*B]
+  double* fermi = nullptr;                      // [n*B]
+  bool pending = false;                         // a trajectory proposal awaits commit
+  int* nt_dev = nullptr;                        // [B]
+  double* dt_dev = nullptr;                     // [B]
+  double *Hold_dev = nullptr, *Hnew_dev = nullptr, *dH_dev = nullptr;  // [B]
+  int* accept_dev = nullptr;                    // [B]
+  int* nacc_dev = nullptr;                      // [B]
+  double* unif_dev = nullptr;                   // [B]
+  double* obs_dev = nullptr;                    // [9*B]
+  unsigned long long seed = 0x9E3779B97F4A7C15ull;
+  unsigned long long rng_counter = 0;
+  // force / observable partial sums
+  int fchunks = 0;              // column chunks per chain
+  cplx* Ppart = nullptr;        // [fchunks * 2N * B]
+  double* hpart = nullptr;      // [fchunks * B]
+  cplx* Pbond = nullptr;        // [2N*B] reduced pair correlators
+  // eigensolver workspace
+  cplx* A = nullptr;            // [n*n*B] work matrix (full Hermitian storage)
+  cplx* V = nullptr;            // [n*n*B] Householder vectors, explicit unit entries, zeros above
+  cplx* ypart = nullptr;        // [NSPLIT*n*B] hemv partial results
+  cplx* P1 = nullptr;           // [NB*B]   W_panel^H v
+  cplx* P2 = nullptr;           // [n*NB*B] V_panel^H v, kept for the T factors
+  cplx* Tf = nullptr;           // [nblk*NB*NB*B] block reflector T factors
+  cplx* tau = nullptr;          // [n*B]
+  double *d = nullptr, *e = nullptr;            // [n*B]
+  cplx* Wbt = nullptr;          // [NB*n*B] back-transform workspace
+  cplx* Wbt2 = nullptr;
+  int nblk = 0;
+  // D&C workspace
+  DcTree tree;
+  std::vector<DcLevelDev> levels;
+  int* leaf_off = nullptr; int* leaf_size = nullptr; int nleaves = 0;
+  double *Z0 = nullptr, *Z1 = nullptr, *S = nullptr;   // [n*n*B]
+  double* Zfinal = nullptr;
+  int* perm = nullptr;          // [n*B]
+  int* ord = nullptr;           // [n*B]
+  double *zvec = nullptr, *dl = nullptr, *wv = nullptr, *dnew = nullptr, *zhat = nullptr, *stau = nullptr;  // [n*B]
+  int *ndl = nullptr, *dfl = nullptr, *sorg = nullptr;   // [n*B]
+  void* rots = nullptr;         // [n*B] DeflRot
+  int* kcnt = nullptr;          // [n*B] indexed by b*n + merge offset
+  int* nrot = nullptr;          // [n*B]
+  double* rho = nullptr;        // [n*B]
+  int* status = nullptr;        // [4] device: [0] leaf failures, [1] secular non-convergence
+  long long launches = 0;
+  long long eigensolves = 0;
+};
+
+// error helpers --------------------------------------------------------------------
+#define DW_CUDA(h, call)                                                              \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      return DWHMC_E_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define DW_LAUNCH_CHECK(h)                                                            \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    (h)->launches++;                                                                  \
+    if (e__ != cudaSuccess) {                                                         \
+      (h)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " at " +  \
+                 __FILE__ + ":" + std::to_string(__LINE__);                           \
+      return DWHMC_E_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define DW_TRY(expr)                    \
+  do {                                  \
+    int rc__ = (expr);                  \
+    if (rc__ != DWHMC_OK) return rc__;  \
+  } while (0)
+
+// stage entry points (each returns a DWHMC_* code) ----------------------------------
+// assemble.cu: full Hermitian BdG matrix of every active chain into h->A
+int dw_assemble(Handle* h, const double* w, const double* par3, const cplx* delta, cplx* A, Mask mask);
+// reference-layout H_base (upper triangle, lower = 0) into out
+int dw_assemble_upper(Handle* h, const double* w, const double* par3, const cplx* delta, cplx* out);
+// hetrd.cu: h->A -> h->d, h->e, h->V, h->tau, h->Tf ; Wscratch is an n*n*B complex scratch
+int dw_hetrd(Handle* h, cplx* Wscratch, Mask mask);
+// stedc.cu: h->d, h->e -> eigenvalues E_out (ascending) and real eigenvectors written as complex into U_out
+int dw_stedc(Handle* h, Mask mask);
+int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask);
+// backtransform.cu: U <- Q U
+int dw_backtransform(Handle* h, cplx* U, Mask mask);
+// A (assembled, destroyed) -> E, U
+int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask);
+
+// generic batched complex GEMM on FP64 tensor cores (gemm_dmma.cu)
+// C = beta*C + alpha * sum_seg opA(A_seg) * opB(B_seg);  opX: 0 = N, 1 = C (conjugate transpose)
+struct ZgemmArgs {
+  int M, N, K;                 // K per segment
+  int nseg;                    // 1 or 2
+  const cplx* A[2]; const cplx* Bm[2];
+  int lda, ldb, ldc;
+  long long sA, sB, sC;        // batch strides (elements)
+  cplx* C;
+  double alpha, beta;
+  int opA, opB;
+  int lower;                   // only tiles touching the lower triangle
+  int batch;
+  Mask mask;
+};
+int dw_zgemm(Handle* h, const ZgemmArgs& a);
+
+// force.cu ---------------------------------------------------------------------------
+// bond correlators of (U, E) -> h->Pbond, h->fermi; then F = -(beta/2J)(Delta - J P) -> h->force.
+// mode 0: force only.  mode 1 (trajectory): also the leapfrog kick / drift that follows force
+// evaluation number `step` (0 = start of trajectory) for chains with step <= nt[b].
+int dw_forces(Handle* h, const double* E, const cplx* U, int mode, int step);
+int dw_total_energy(Handle* h, const double* E, double* out_dev);   // out_dev [B]
+int dw_observables(Handle* h, double* out_dev);                     // out_dev [9*B], uses E_cur/U_cur
+int dw_refresh_momentum(Handle* h);                                 // Philox N(0, m)
+int dw_uniforms(Handle* h);                                         // Philox U[0,1) -> h->unif_dev
+int dw_begin_trajectory(Handle* h);                                 // backup Delta
+int dw_metropolis(Handle* h, bool use_uniforms);                    // dH, unif -> accept_dev
+int dw_commit_dev(Handle* h);                                       // accept_dev -> swap / restore
+int dw_dH(Handle* h);                                               // dH = Hnew - Hold
