@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- HMC trajectories/s of the molecular-dynamics force path at L=24 (BASELINE.json).
+
+One "step" = one hmc_sweep! (src/HMC.jl:71-144) over a batch of independent chains: momentum
+refresh, H_old, Nt leapfrog steps (each: BdG assembly, 2N x 2N Hermitian eigendecomposition,
+bond-correlator force, kick/drift), H_new, Metropolis, commit.  Workload = the per-GPU shard of
+BASELINE config 3 (L=24 disordered T-scan, 32 T x 16 seeds = 512 chains over 8 GPUs = 64 chains
+per GPU), Nt_measure = 6 and the physics of scripts/batch_scan_T.jl:10-36.  Weak scaling: every
+rank owns 64 chains; there is no data-path collective (chains are independent), only an
+end-of-run gather of the observables table.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
+  python bench.py --impl reference ...                         CPU oracle (the reference's algorithm,
+                                                               LAPACK zheevr) on the host cores
+Prints ONE JSON line (rank 0)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hybrid-monte-carlo-for-d-wave-sc_b200"))
+
+PHYS = dict(t=1.0, tp=-0.35, mu=-1.08, W=1.0, n_imp=0.05, J=0.8, mass=1.0)   # scripts/batch_scan_T.jl:10-19
+METRIC = "HMC trajectories/sec at L=24 (disordered T-scan shard, Nt=6)"
+
+
+def temperatures(n_points=32):
+    return 10.0 ** np.linspace(-4, 3, n_points)
+
+
+def chain_setup(L, chain_ids, n_seeds=16):
+    """(beta, disorder, Delta0) of the global chains `chain_ids` of the 32 T x 16 seed scan;
+    seed = 3e6 + 1e3 * i_point + i_seed, NumPy PCG64."""
+    N = L * L
+    Ts = temperatures()
+    betas, ws, Ds = [], [], []
+    for c in chain_ids:
+        ip, iseed = divmod(int(c), n_seeds)
+        ip %= len(Ts)
+        rng = np.random.Generator(np.random.PCG64(3_000_000 + 1000 * ip + iseed))
+        w = np.zeros(N)
+        w[rng.permutation(N)[:int(np.rint(N * PHYS["n_imp"]))]] = PHYS["W"]
+        re, im = rng.random((N, 2)), rng.random((N, 2))
+        betas.append(1.0 / Ts[ip]); ws.append(w); Ds.append((((re - 0.5) + 1j * (im - 0.5)) * 0.1).T)
+    return np.array(betas), np.stack(ws), np.stack(Ds)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({nm for r in self.rows if len(r) >= 6 for nm, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def fp64_peak_tflops(device):
+    """No FP64 entry in MEASURED_PEAKS.json: measure cuBLAS DGEMM (torch.matmul fp64, 4096^3) live."""
+    import torch
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=device)
+    for _ in range(2):
+        a @ b
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = max(best, 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def cpu_oracle_sample(L, Nt, n_traj=1, threads=None):
+    """Time the CPU restatement (oracle = reference algorithm, LAPACK zheevr via SciPy) on a bounded
+    sample: n_traj trajectories of chain 0 of the workload.  Returns (traj/s, cores, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dwhmc_oracle as orc
+    cores = len(os.sched_getaffinity(0))
+    beta, w, D0 = chain_setup(L, [8 * 16])          # a mid-scan temperature point
+    p = orc.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], PHYS["n_imp"], float(beta[0]), PHYS["J"],
+                            PHYS["mass"])
+    st = orc.SimulationState(w[0], D0[0].T.copy(), np.zeros((L * L, 2), complex))
+    c = orc.initialize_cache(p)
+    orc.init_static_H(c, p, st); orc.update_H_BdG(c, p, st); orc.diagonalize_H_BdG(c, p)
+    rng = np.random.Generator(np.random.PCG64(1))
+    dt = orc.calc_optimal_dt(p.beta, p.J, p.mass, Nt)
+    t0 = time.perf_counter()
+    for _ in range(n_traj):
+        orc.hmc_sweep(c, p, st, Nt=Nt, dt=dt, rng=rng)
+    el = time.perf_counter() - t0
+    return n_traj / el, cores, (f"{n_traj} trajectory(ies) of 1 chain, L={L}, Nt={Nt}, one process, "
+                                f"OpenBLAS threads = all {cores} visible cores (the reference's shipped mode)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L, Nt = args.L, args.nt
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_sample(L, Nt, 1)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, cores, desc = cpu_oracle_sample(L, Nt, 1)
+        vals.append(v)
+    el = time.perf_counter() - t0
+    value = len(vals) / sum(1.0 / v for v in vals)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args),
+           "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": desc},
+           "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "Julia is not installed, so the reference cannot run; this arm times oracle/dwhmc_oracle.py, the "
+                   "NumPy/SciPy restatement that calls the same LAPACK zheevr; each step = 1 trajectory of 1 chain",
+           "wall_s": el}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"L={args.L} disordered T-scan shard (BASELINE config 3): {args.chains} chains/GPU "
+                        f"(32 T x 16 seeds over 8 GPUs), n=2N={2 * args.L ** 2}, Nt={args.nt}, t'=-0.35 mu=-1.08 W=1 "
+                        f"n_imp=0.05 J=0.8",
+            "chains_per_gpu": args.chains, "L": args.L, "Nt": args.nt,
+            "l2": "inputs larger than L2 (per-step working set > 5 GB vs 126 MB L2)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dwhmc
+    from dwhmc.parallel import gather_table, shard_chains
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L, B, Nt, K, W = args.L, args.chains, args.nt, args.steps, max(args.warmup, 3)
+    N, n = L * L, 2 * L * L
+    n_chains = B * world
+    ids = shard_chains(n_chains, rank, world)
+    beta, w, D0 = chain_setup(L, ids)
+    cb = dwhmc.ChainBatch(B, L, L, device=local)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], beta, PHYS["J"], PHYS["mass"])
+    cb.set_disorder(w); cb.set_field(D0)
+    cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    cb.seed(1234 + rank)
+    dt = np.array([dwhmc.calc_optimal_dt(b, PHYS["J"], PHYS["mass"], Nt) for b in beta])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput: K sweeps, RNG on device, no host transfer inside
+    cb.run_sweeps(W, Nt, dt)
+    barrier()
+    cb.reset_timers()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        nacc, dH, _ = cb.run_sweeps(K, Nt, dt)
+        ms_dev = cb.last_elapsed_ms()          # CUDA events on the library's stream
+        barrier()
+        wall = time.perf_counter() - t0
+    launches = int(cb.timers()["launches"])
+    ms_dev = max_over_ranks(ms_dev)
+    value = n_chains * K / (ms_dev * 1e-3)
+
+    # ---- end to end through the public batched API with host buffers
+    rng = np.random.Generator(np.random.PCG64(99 + rank))
+    pin = torch.empty((B, 2, N), dtype=torch.complex128).pin_memory()
+    pi_host = pin.numpy()
+    nt_arr = np.full(B, Nt, dtype=np.int32)
+    h2d = pi_host.nbytes + 8 * B + 4 * B + 8 * B
+    d2h = 4 * B + 8 * B + 8 * 9 * B
+    sq = np.sqrt(PHYS["mass"])
+
+    def e2e_step():
+        pi_host[...] = (rng.standard_normal((B, 2, N)) + 1j * rng.standard_normal((B, 2, N))) * sq
+        u = rng.random(B)
+        acc, dHs = cb.hmc_sweep(nt_arr, dt, pi0=pi_host, uniforms=u)
+        obs = cb.measure_observables()
+        return acc, dHs, obs
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        acc, dHs, obs = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_chains * K / e2e_s
+
+    # ---- stage breakdown for the roofline (separate profiled pass; event pairs per stage)
+    cb.set_profiling(True); cb.reset_timers()
+    cb.run_sweeps(1, Nt, dt)
+    tm = cb.timers()
+    cb.set_profiling(False)
+    eig_ms = tm["tridiagonalize_ms"] + tm["stedc_ms"] + tm["backtransform_ms"]
+    n_solves = tm["eigensolves"]                       # batched solves (each = B matrices)
+    flops_per_solve = B * (40.0 / 3.0) * n ** 3        # 40/3 n^3 per eigendecomposition
+    eig_tflops = n_solves * flops_per_solve / (eig_ms * 1e-3) / 1e12
+    hemv_bytes = B * 16.0 * sum((n - j - 1) ** 2 for j in range(n - 1))
+    hemv_gbs = n_solves * hemv_bytes / (tm["hemv_ms"] * 1e-3) / 1e9
+
+    # ---- end-of-run gather of the observables table (the only collective of the run)
+    table = gather_table(np.concatenate([dHs[:, None], acc[:, None].astype(float), obs], axis=1), ids, n_chains,
+                         dist if world > 1 else None, dev if world > 1 else None)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        fp64_peak = fp64_peak_tflops(dev)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        cpu_v, cores, desc = cpu_oracle_sample(L, Nt, 2)
+        out = {
+            "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "force_evals_per_s": value * (Nt + 1), "eigensolves_per_s": value * Nt,
+            "acceptance": float(nacc.mean() / K), "wall_s_timed_region": wall,
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "ChainBatch.hmc_sweep(pi0, uniforms from pinned host) + measure_observables -> host"},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "kernel": "batched Hermitian eigensolve (hetrd + stedc + back-transform)",
+                         "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eig_tflops / fp64_peak,
+                         "traffic": None,
+                         "peak_source": "measured live: torch.matmul fp64 4096^3 (cuBLAS DGEMM); MEASURED_PEAKS.json "
+                                        "has no FP64 entry",
+                         "algorithmic_flops_per_launch": flops_per_solve,
+                         "share_of_step": eig_ms / (eig_ms + tm["assemble_ms"] + tm["force_ms"])},
+            "roofline_hbm": {"bound": "hbm", "kernel": "hemv_kernel (trailing-matrix product of the tridiagonalisation)",
+                             "achieved": hemv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hemv_gbs / hbm_peak,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback",
+                             "algorithmic_bytes_per_solve": hemv_bytes, "share_of_eigensolve": tm["hemv_ms"] / eig_ms},
+            "stage_ms_per_sweep": {k: v for k, v in tm.items() if k.endswith("_ms")},
+            "cpu_baseline": {"value": cpu_v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": desc},
+            "gathered_table_shape": list(table.shape),
+        }
+        print(json.dumps(out), flush=True)
+    cb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=24)
+    ap.add_argument("--chains", type=int, default=64, help="chains per GPU")
+    ap.add_argument("--nt", type=int, default=6, help="leapfrog steps (Nt_measure, scripts/batch_scan_T.jl:33)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

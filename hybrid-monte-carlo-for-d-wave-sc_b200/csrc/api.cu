@@ -113,6 +113,8 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaEventCreate(&h->ev_begin);
+  cudaEventCreate(&h->ev_end);
   const size_t nB = (size_t)n * B, nnB = (size_t)n * n * B;
   h->nblk = (n - 1 + DW_NB - 1) / DW_NB;
   h->fchunks = (n + DW_FCHUNK - 1) / DW_FCHUNK;
@@ -183,6 +185,8 @@ int dwhmc_destroy(dwhmc_handle hh) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_begin) cudaEventDestroy(h->ev_begin);
+  if (h->ev_end) cudaEventDestroy(h->ev_end);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete static_cast<dwhmc_handle_s*>(hh);
   return DWHMC_OK;
@@ -419,6 +423,7 @@ int dwhmc_run_sweeps(dwhmc_handle hh, int n_sweeps, const int32_t* Nt, const dou
   int max_nt = 0;
   DW_TRY(load_steps(h, Nt, dt, &max_nt));
   DW_CUDA(h, cudaMemsetAsync(h->nacc_dev, 0, sizeof(int) * h->B, h->stream));
+  DW_CUDA(h, cudaEventRecord(h->ev_begin, h->stream));
   double* obs_all = nullptr;
   const size_t per = (size_t)DWHMC_NOBS * h->B;
   if (obs && n_sweeps > 0) DW_CUDA(h, cudaMalloc(&obs_all, sizeof(double) * per * n_sweeps));
@@ -429,6 +434,13 @@ int dwhmc_run_sweeps(dwhmc_handle hh, int n_sweeps, const int32_t* Nt, const dou
     if (rc == DWHMC_OK) rc = dw_metropolis(h, true);
     if (rc == DWHMC_OK) rc = dw_commit_dev(h);
     if (rc == DWHMC_OK && obs_all) rc = dw_observables(h, obs_all + per * s);
+  }
+  if (rc == DWHMC_OK) {
+    cudaEventRecord(h->ev_end, h->stream);
+    cudaEventSynchronize(h->ev_end);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
+    h->last_ms = ms;
   }
   if (rc == DWHMC_OK && obs_all) rc = d2h(h, obs, obs_all, sizeof(double) * per * n_sweeps);
   if (obs_all) { cudaStreamSynchronize(h->stream); cudaFree(obs_all); }
@@ -447,6 +459,12 @@ int dwhmc_get_timers(dwhmc_handle hh, double* out) {
   for (int i = 0; i < 8; ++i) out[i] = h->timers[i];
   out[5] = (double)h->eigensolves;
   out[6] = (double)h->launches;
+  return DWHMC_OK;
+}
+int dwhmc_last_elapsed_ms(dwhmc_handle hh, double* out) {
+  H_ENTER(hh);
+  if (!out) BADARG("dwhmc_last_elapsed_ms: NULL");
+  *out = h->last_ms;
   return DWHMC_OK;
 }
 int dwhmc_reset_timers(dwhmc_handle hh) {

@@ -11,7 +11,7 @@
 
 namespace {
 
-// LogExpFunctions 0.3.29, Float64 branches (see oracle/dwhmc_oracle.py for the restatement)
+// LogExpFunctions 0.3.29, Float64 branches
 __device__ __forceinline__ double logistic(double x) {
   if (x < -744.4400719213812) return 0.0;
   if (x > 36.7368005696771) return 1.0;

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(CT) colstep_kernel(ColArgs g) {
   cplx* rowW = sw + g.n;                          // [NB]
   cplx* rowV = rowW + DW_NB;                      // [NB]
   cplx* red = rowV + DW_NB;                       // [32]
-  __shared__ cplx s_tau, s_scale;
+  __shared__ cplx s_scale;
 
   const int n = g.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t mat = (size_t)b * n * n;
@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(CT) colstep_kernel(ColArgs g) {
       g.d[(size_t)b * n + j] = a0.x;
       g.e[(size_t)b * n + j] = beta;
       g.tau[(size_t)b * n + j] = tau;
-      s_tau = tau;
       s_scale = scale;
     }
     __syncthreads();
@@ -281,8 +280,16 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       const int m = n - j - 1;
       const int cs = (m + DW_NSPLIT - 1) / DW_NSPLIT;
       dim3 grid((m + HT - 1) / HT, DW_NSPLIT, B);
+      if (h->profiling) cudaEventRecord(h->ev_begin, h->stream);
       hemv_kernel<<<grid, HT, sizeof(cplx) * cs, h->stream>>>(h->A, h->V, h->ypart, n, B, j, mask);
       DW_LAUNCH_CHECK(h);
+      if (h->profiling) {
+        cudaEventRecord(h->ev_end, h->stream);
+        cudaEventSynchronize(h->ev_end);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
+        h->timers[7] += ms;
+      }
     }
     const int j1 = j0 + pn;
     g.j = j1; g.finish_prev = 1; g.make_ref = 0;

@@ -39,7 +39,8 @@ struct Handle {
   std::string err;
   bool profiling = false;
   double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
+  double last_ms = 0.0;          // device time of the last dwhmc_run_sweeps (events on `stream`)
   std::vector<void*> allocs;    // everything cudaMalloc'ed, for destroy
 
   // lattice (device, 0-based int32, [dir * N + site])

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "dwhmc_run_sweeps": [_vp, _i, _ip, _dp, _ip, _dp, _dp],
     "dwhmc_get_timers": [_vp, _dp],
     "dwhmc_reset_timers": [_vp],
+    "dwhmc_last_elapsed_ms": [_vp, _dp],
     "dwhmc_set_profiling": [_vp, _i],
     "dwhmc_debug_tridiagonalize": [_vp, _dp, _dp],
     "dwhmc_debug_stedc": [_vp, _dp, _dp, _dp, _dp],

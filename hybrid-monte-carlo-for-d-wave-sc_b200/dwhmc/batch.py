@@ -213,12 +213,18 @@ class ChainBatch:
     def reset_timers(self):
         check(lib.dwhmc_reset_timers(self._h), self._h)
 
+    def last_elapsed_ms(self) -> float:
+        """Device time of the last run_sweeps (CUDA events on the library's stream)."""
+        out = np.zeros(1)
+        check(lib.dwhmc_last_elapsed_ms(self._h, dptr(out)), self._h)
+        return float(out[0])
+
     def timers(self):
         out = np.zeros(8)
         check(lib.dwhmc_get_timers(self._h, dptr(out)), self._h)
         keys = ("assemble_ms", "tridiagonalize_ms", "stedc_ms", "backtransform_ms", "force_ms", "eigensolves",
-                "launches", "_")
-        return dict(zip(keys[:7], out[:7]))
+                "launches", "hemv_ms")
+        return dict(zip(keys, out))
 
     # ---- eigensolver stage entry points (parity tests)
     def debug_tridiagonalize(self):

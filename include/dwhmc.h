@@ -134,9 +134,13 @@ int dwhmc_run_sweeps(dwhmc_handle h, int n_sweeps, const int32_t* Nt, const doub
 /* device time (ms, CUDA events on the handle's stream) spent in each stage since
  * the last reset: [0] assemble, [1] tridiagonalise, [2] tridiagonal D&C,
  * [3] back-transform, [4] force/energy/update kernels, [5] total eigensolves
- * (count), [6] kernel launches (count).  out: double[8]. */
+ * (count), [6] kernel launches (count), [7] the trailing-matrix hemv kernels alone
+ * (part of [1]).  out: double[8].  Stage times accumulate only while profiling is on. */
 int dwhmc_get_timers(dwhmc_handle h, double* out);
 int dwhmc_reset_timers(dwhmc_handle h);
+/* device time (ms) of the sweeps of the last dwhmc_run_sweeps call, measured with CUDA events
+ * recorded on the handle's stream around the enqueued work (excludes the final D2H copies) */
+int dwhmc_last_elapsed_ms(dwhmc_handle h, double* out);
 /* enable (1) / disable (0) per-stage event timing (adds stream synchronisation) */
 int dwhmc_set_profiling(dwhmc_handle h, int on);
 
@@ -145,8 +149,9 @@ int dwhmc_set_profiling(dwhmc_handle h, int on);
  * solve a caller-supplied tridiagonal problem (d, e) -> w (double[n*B]), Z (double[n*n*B]). */
 int dwhmc_debug_tridiagonalize(dwhmc_handle h, double* d, double* e);
 int dwhmc_debug_stedc(dwhmc_handle h, const double* d, const double* e, double* w, double* Z);
-/* diagonalise caller-supplied Hermitian matrices (complex[n*n*B], lower triangle
- * read) -> E (double[n*B]), U (complex[n*n*B]); does not touch the chain state. */
+/* diagonalise caller-supplied Hermitian matrices (complex[n*n*B], full storage: both
+ * triangles are read) -> E (double[n*B]), U (complex[n*n*B]); does not touch Delta, pi,
+ * E_n or U of the chains (it uses the proposal buffers). */
 int dwhmc_debug_heev(dwhmc_handle h, const double* A, double* E, double* U);
 
 #ifdef __cplusplus

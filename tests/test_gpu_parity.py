@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the reference-shaped host API) against
+the CPU oracle and the committed golden vectors.  Tolerances follow BASELINE.json's north star:
+1e-10 relative in FP64 for energies, forces and dH (dH relative to |H_old|).
+Eigenvectors are never compared column by column (phases / degenerate subspaces are arbitrary);
+the residual, unitarity and every gauge-invariant quantity are."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import dwhmc_oracle as orc  # noqa: E402  (checker only)
+
+RTOL = 1e-10
+PHYS = dict(t=1.0, tp=-0.35, mu=-1.08, W=1.0, J=0.8, mass=1.0)
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def dw():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import dwhmc
+    return dwhmc
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors_single_chain(dw, path):
+    """Reads like the reference's own call sequence (src/Simulation.jl:81-86, then hmc_sweep!)."""
+    g = np.load(path)
+    p = dw.ModelParameters(int(g["Lx"]), int(g["Ly"]), PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"],
+                           float(g["n_imp"]), float(g["beta"]), PHYS["J"], PHYS["mass"])
+    state = dw.SimulationState(g["disorder"].copy(), g["Delta0"].copy(), np.zeros_like(g["Delta0"]))
+    cache = dw.initialize_cache(p)
+    dw.init_static_H(cache, p, state)
+    dw.update_H_BdG(cache, p, state)
+    dw.diagonalize_H_BdG(cache, p)
+    scale = np.max(np.abs(g["E0"]))
+    assert np.max(np.abs(cache.E_n - g["E0"])) <= 1e-12 * scale
+    dw.compute_forces(cache, p, state)
+    assert rel(cache.forces, g["F0"]) <= RTOL
+    obs = np.array(dw.measure_observables(cache, p, state))
+    assert np.allclose(obs, g["obs0"], rtol=1e-9, atol=1e-11)
+    for k in range(len(g["u"])):
+        acc, dH = dw.hmc_sweep(cache, p, state, Nt=int(g["Nt"]), dt=float(g["dt"]), pi0=g["pi0"][k],
+                               uniform=float(g["u"][k]))
+        Hscale = max(abs(float(g["H_old"][k])), 1.0)
+        assert abs(dH - g["dH"][k]) <= RTOL * Hscale
+        assert acc == bool(g["accepted"][k])
+        assert np.max(np.abs(state.Delta - g["Delta_end"][k])) <= 1e-10
+        assert np.max(np.abs(state.pi - g["pi_end"][k])) <= 1e-9 * max(1.0, np.max(np.abs(g["pi_end"][k])))
+        assert np.max(np.abs(cache.E_n - g["E_end"][k])) <= 1e-11 * scale
+        obs = np.array(dw.measure_observables(cache, p, state))
+        assert np.allclose(obs, g["obs_end"][k], rtol=1e-8, atol=1e-10)
+    cache.batch.close()
+
+
+def make_batch(dw, L, betas, n_imp, seed0, Nt=None):
+    Lx, Ly = (L, L) if isinstance(L, int) else L
+    B = len(betas)
+    ps, sts, cs = [], [], []
+    for b, beta in enumerate(betas):
+        p = orc.ModelParameters(Lx, Ly, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], n_imp, float(beta), PHYS["J"],
+                                PHYS["mass"])
+        _, st, c = orc.make_chain(p, seed0 + b)
+        ps.append(p); sts.append(st); cs.append(c)
+    cb = dw.ChainBatch(B, Lx, Ly)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], np.asarray(betas, float), PHYS["J"], PHYS["mass"])
+    cb.set_disorder(np.stack([s.disorder_pot for s in sts]))
+    cb.set_field(np.stack([s.Delta for s in sts]))
+    cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    return cb, ps, sts, cs
+
+
+def test_H_base_bit_exact(dw):
+    cb, ps, sts, cs = make_batch(dw, (6, 10), [2.0, 20.0], 0.05, 300)
+    H = cb.get_H()
+    for b in range(2):
+        assert np.array_equal(H[b].T, cs[b].H_base)       # upper triangle, lower = 0, as the reference stores it
+    cb.close()
+
+
+def test_batched_sweeps_match_oracle_mixed_Nt_and_beta(dw):
+    """Chains with different temperatures, disorder seeds and leapfrog step counts in one batch."""
+    betas = [0.5, 5.0, 20.0, 100.0, 1000.0]
+    cb, ps, sts, cs = make_batch(dw, 8, betas, 0.05, 400)
+    B = len(betas)
+    Nt = np.array([2, 6, 3, 5, 4], dtype=np.int32)
+    dt = np.array([orc.calc_optimal_dt(p.beta, p.J, p.mass, int(k)) for p, k in zip(ps, Nt)]) * 0.5
+    n_acc = 0
+    for it in range(4):
+        pi0 = np.stack([orc.draw_momentum(ps[b], np.random.default_rng(900 + 10 * it + b)) for b in range(B)])
+        u = np.random.default_rng(990 + it).random(B)
+        acc, dH = cb.hmc_sweep(Nt, dt, pi0=pi0, uniforms=u)
+        D, Pi, E = cb.get_field(), cb.get_momentum(), cb.get_eigenvalues()
+        for b in range(B):
+            a_r, dH_r, Ho, Hn = orc.hmc_sweep(cs[b], ps[b], sts[b], Nt=int(Nt[b]), dt=float(dt[b]), pi0=pi0[b],
+                                              uniform=float(u[b]), return_energies=True)
+            assert abs(dH[b] - dH_r) <= RTOL * max(abs(Ho), 1.0), (it, b)
+            assert bool(acc[b]) == a_r
+            assert np.max(np.abs(D[b].T - sts[b].Delta)) <= 1e-10
+            assert np.max(np.abs(Pi[b].T - sts[b].pi)) <= 1e-9 * max(1.0, np.max(np.abs(sts[b].pi)))
+            assert np.max(np.abs(E[b] - cs[b].E_n)) <= 1e-11 * np.max(np.abs(cs[b].E_n))
+            n_acc += int(a_r)
+    assert 0 < n_acc < 4 * B            # both the accept and the restore branch were exercised
+    O = cb.measure_observables()
+    for b in range(B):
+        assert np.allclose(O[b], orc.measure_observables(cs[b], ps[b], sts[b]), rtol=1e-8, atol=1e-10)
+    cb.close()
+
+
+def test_trajectory_commit_split_keeps_lazy_uniform(dw):
+    cb, ps, sts, cs = make_batch(dw, 4, [5.0, 5.0], 0.0, 500)
+    Nt, dt = 4, 0.05
+    pi0 = np.stack([orc.draw_momentum(ps[b], np.random.default_rng(7 + b)) for b in range(2)])
+    Ho, Hn, dH = cb.trajectory(Nt, dt, pi0=pi0)
+    with pytest.raises(dw.DwhmcError):          # a second proposal before commit is a sequence error
+        cb.trajectory(Nt, dt, pi0=pi0)
+    D_prop = cb.get_field()
+    cb.commit([1, 0])
+    D = cb.get_field()
+    assert np.array_equal(D[0], D_prop[0])                       # accepted: proposal kept
+    assert np.array_equal(D[1].T, sts[1].Delta)                  # rejected: restored bit-exactly
+    E = cb.get_eigenvalues()
+    assert np.max(np.abs(E[1] - cs[1].E_n)) <= 1e-12 * np.max(np.abs(cs[1].E_n))
+    for b in range(2):
+        _, dH_r, Ho_r, Hn_r = orc.hmc_sweep(cs[b], ps[b], sts[b], Nt=Nt, dt=dt, pi0=pi0[b], uniform=0.0 if b == 0 else 1.0,
+                                            return_energies=True)
+        assert abs(Ho[b] - Ho_r) <= 1e-11 * max(abs(Ho_r), 1) and abs(dH[b] - dH_r) <= RTOL * max(abs(Ho_r), 1)
+    with pytest.raises(dw.DwhmcError):
+        cb.commit([1, 1])
+    cb.close()
+
+
+def test_force_is_gradient_of_action_config2_shape(dw):
+    """BASELINE config 2: disordered L=16, 64 chains in one batch; dS/dRe(D) = -2 Re F,
+    dS/dIm(D) = -2 Im F by central differences (h = 1e-5) on 16 random bond components."""
+    B, L, h = 64, 16, 1e-5
+    N = L * L
+    rng = np.random.default_rng(16)
+    betas = np.logspace(-1, 2, B)
+    cb = dw.ChainBatch(B, L, L)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], betas, PHYS["J"], PHYS["mass"])
+    w = np.zeros((B, N))
+    for b in range(B):
+        w[b, rng.permutation(N)[:13]] = PHYS["W"]
+    D0 = ((rng.random((B, 2, N)) - 0.5) + 1j * (rng.random((B, 2, N)) - 0.5)) * 0.1
+    cb.set_disorder(w); cb.set_momentum(np.zeros((B, 2, N), complex))
+
+    def action(D):
+        cb.set_field(D); cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+        return cb.compute_total_energy()
+
+    action(D0)
+    cb.compute_forces()
+    F = cb.get_forces()
+    # chain 0 against the oracle as well
+    p = orc.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.05, float(betas[0]), PHYS["J"], PHYS["mass"])
+    st = orc.SimulationState(w[0], D0[0].T.copy(), np.zeros((N, 2), complex))
+    c = orc.initialize_cache(p)
+    orc.init_static_H(c, p, st); orc.update_H_BdG(c, p, st); orc.diagonalize_H_BdG(c, p); orc.compute_forces(c, p, st)
+    assert rel(F[0].T, c.forces) <= RTOL
+    for _ in range(16):
+        d, i = int(rng.integers(2)), int(rng.integers(N))
+        for part, comp in ((1.0, "real"), (1j, "imag")):
+            Dp, Dm = D0.copy(), D0.copy()
+            Dp[:, d, i] += part * h
+            Dm[:, d, i] -= part * h
+            fd = (action(Dp) - action(Dm)) / (2 * h)
+            an = -2.0 * getattr(F[:, d, i], comp)
+            assert np.all(np.abs(fd - an) <= 2e-6 * np.maximum(np.abs(an), 1.0)), (d, i, comp)
+    cb.close()
+
+
+def test_leapfrog_reversibility(dw):
+    cb, ps, sts, cs = make_batch(dw, 8, [10.0, 50.0], 0.05, 600)
+    D0 = cb.get_field()
+    pi0 = np.stack([orc.draw_momentum(ps[b], np.random.default_rng(3 + b)) for b in range(2)])
+    Nt, dt = 5, 0.02
+    cb.trajectory(Nt, dt, pi0=pi0); cb.commit([1, 1])
+    cb.trajectory(Nt, dt, pi0=-cb.get_momentum()); cb.commit([1, 1])
+    assert np.max(np.abs(cb.get_field() - D0)) <= 1e-11
+    assert np.max(np.abs(cb.get_momentum() + pi0.transpose(0, 2, 1))) <= 1e-10
+    cb.close()
+
+
+@pytest.mark.parametrize("L,B", [(16, 4), (24, 2)])
+def test_eigensolver_properties_full_size(dw, L, B):
+    """Size-independent properties at the benchmark sizes: residual, unitarity, +-E symmetry
+    (particle-hole), trace, and agreement with LAPACK eigenvalues."""
+    n = 2 * L * L
+    cb, ps, sts, cs = make_batch(dw, L, np.logspace(0, 2, B), 0.05, 700)
+    E, U = cb.get_eigenvalues(), cb.get_eigenvectors()
+    for b in range(B):
+        Hf = orc.full_hermitian(cs[b]); Ub = U[b].T
+        nrm = np.max(np.abs(cs[b].E_n))
+        assert np.max(np.abs(E[b] - cs[b].E_n)) <= 1e-12 * nrm
+        assert np.max(np.abs(Hf @ Ub - Ub * E[b])) <= 1e-12 * nrm
+        assert np.max(np.abs(Ub.conj().T @ Ub - np.eye(n))) <= 1e-12
+        assert np.max(np.abs(E[b] + E[b][::-1])) <= 1e-12 * nrm
+        assert abs(np.sum(E[b])) <= 1e-10 * nrm
+        assert np.all(np.diff(E[b]) >= 0)
+    cb.compute_forces()
+    F = cb.get_forces()
+    for b in range(B):
+        orc.compute_forces(cs[b], ps[b], sts[b])
+        assert rel(F[b].T, cs[b].forces) <= RTOL
+    cb.close()
+
+
+def test_degenerate_and_extreme_spectra(dw):
+    """Clean lattice (massively degenerate), beta from 1e-3 to 1e5 (f(E) from flat to a step)."""
+    betas = [1e-3, 1.0, 1e3, 1e5]
+    cb, ps, sts, cs = make_batch(dw, 8, betas, 0.0, 800)
+    cb.compute_forces()
+    F = cb.get_forces()
+    pi = np.zeros((4, 2, 64), complex)
+    cb.set_momentum(pi)
+    Eg = cb.compute_total_energy()
+    for b in range(4):
+        orc.compute_forces(cs[b], ps[b], sts[b])
+        assert rel(F[b].T, cs[b].forces) <= RTOL
+        Er = orc.compute_total_energy(cs[b], ps[b], sts[b])
+        assert abs(Eg[b] - Er) <= 1e-12 * max(abs(Er), 1.0)
+    # zero field: D = 0, the BdG matrix is block diagonal with exactly paired +-E
+    cb.set_field(np.zeros((4, 2, 64), complex)); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    E = cb.get_eigenvalues()
+    assert np.max(np.abs(E + E[:, ::-1])) <= 1e-13 * np.max(np.abs(E))
+    cb.close()
+
+
+def test_debug_stages(dw):
+    import scipy.linalg as sl
+    B, L = 2, 6
+    n = 2 * L * L
+    rng = np.random.default_rng(1)
+    cb = dw.ChainBatch(B, L, L)
+    A = rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))
+    A = A + A.conj().transpose(0, 2, 1)
+    E, U = cb.debug_heev(A.transpose(0, 2, 1))
+    for b in range(B):
+        Ub = U[b].T
+        assert np.max(np.abs(E[b] - np.linalg.eigvalsh(A[b]))) <= 1e-12 * np.max(np.abs(E[b]))
+        assert np.max(np.abs(A[b] @ Ub - Ub * E[b])) <= 1e-12 * np.max(np.abs(E[b]))
+    for name, d, e in (("wilkinson", np.abs(np.arange(n) - n // 2).astype(float), np.ones(n - 1)),
+                       ("zeros", np.zeros(n), np.zeros(n - 1)),
+                       ("split", rng.standard_normal(n), np.where(np.arange(n - 1) % 7 == 0, 0.0, 1.0)),
+                       ("clustered", 1 + 1e-10 * rng.standard_normal(n), 1e-10 * rng.standard_normal(n - 1))):
+        w, Z = cb.debug_stedc(np.tile(d, (B, 1)), np.tile(e, (B, 1)))
+        wr = sl.eigh_tridiagonal(d, e, eigvals_only=True)
+        T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+        for b in range(B):
+            Zb = Z[b].T
+            nrm = max(np.max(np.abs(wr)), 1e-300)
+            assert np.max(np.abs(w[b] - wr)) <= 5e-14 * nrm, name
+            assert np.max(np.abs(Zb.T @ Zb - np.eye(n))) <= 5e-14, name
+            assert np.max(np.abs(T @ Zb - Zb * w[b])) <= 5e-14 * nrm, name
+    cb.close()
+
+
+def test_error_behaviour(dw):
+    with pytest.raises(dw.DwhmcError):
+        dw.ChainBatch(1, 2, 2)                       # L < 3: neighbours collide
+    cb = dw.ChainBatch(1, 4, 4)
+    with pytest.raises(dw.DwhmcError):
+        cb.compute_total_energy()                    # parameters not set
+    cb.set_params(1.0, -0.35, -1.08, 5.0, 0.8, 1.0)
+    with pytest.raises(dw.DwhmcError):
+        cb.hmc_sweep(0, 0.1)                         # Nt >= 1
+    with pytest.raises(dw.DwhmcError):
+        cb.commit([1])                               # nothing pending
+    # NaN energy rejects (src/HMC.jl:128) and the restore branch runs
+    cb.set_field(np.full((1, 2, 16), 0.01 + 0j)); cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    pi0 = np.full((1, 2, 16), np.nan + 0j)
+    try:
+        acc, dH = cb.hmc_sweep(2, 0.1, pi0=pi0, uniforms=[0.0])
+        assert not acc[0] and np.isnan(dH[0])
+    except dw.EigenConvergenceError:
+        pass                                         # LAPACKException twin is also acceptable for a NaN matrix
+    cb.close()
+
+
+def test_stale_cache_quirk(dw):
+    """The reference lets callers run hmc_sweep! on a cache that was never diagonalised
+    (scripts/benchmark_clean.jl:82-88): the first trajectory starts from E_n = 0, U = 0."""
+    p = orc.ModelParameters(4, 4, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.0, 5.0, PHYS["J"], PHYS["mass"])
+    rng = np.random.Generator(np.random.PCG64(11))
+    st = orc.initialize_state(p, rng)
+    c = orc.initialize_cache(p)
+    orc.init_static_H(c, p, st)
+    pi0 = orc.draw_momentum(p, rng)
+    cb = dw.ChainBatch(1, 4, 4)
+    cb.set_params(p.t, p.tp, p.mu, p.beta, p.J, p.mass)
+    cb.set_disorder(st.disorder_pot[None]); cb.set_field(st.Delta[None]); cb.init_static_H()
+    acc, dH = cb.hmc_sweep(3, 0.1, pi0=pi0[None], uniforms=[0.5])
+    a_r, dH_r = orc.hmc_sweep(c, p, st, Nt=3, dt=0.1, pi0=pi0, uniform=0.5)
+    assert abs(dH[0] - dH_r) <= 1e-9 * max(abs(dH_r), 1.0) and bool(acc[0]) == a_r
+    cb.close()
+
+
+def test_device_rng_statistics(dw):
+    """Throughput mode (Philox momenta / uniforms on device): <exp(-dH)> = 1 and momenta ~ N(0, m)."""
+    B, L = 64, 4
+    cb = dw.ChainBatch(B, L, L)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], 5.0, PHYS["J"], 2.0)
+    rng = np.random.default_rng(5)
+    cb.set_disorder(np.zeros((B, 16)))
+    cb.set_field(((rng.random((B, 2, 16)) - 0.5) + 1j * (rng.random((B, 2, 16)) - 0.5)) * 0.1)
+    cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    cb.seed(1234)
+    dt = orc.calc_optimal_dt(5.0, 0.8, 2.0, 8)
+    cb.run_sweeps(20, 8, dt)                        # thermalise
+    vals, accs = [], 0
+    for _ in range(10):
+        nacc, dH, obs = cb.run_sweeps(1, 8, dt, observables=True)
+        vals.append(np.exp(-dH)); accs += nacc.sum()
+        assert obs.shape == (1, B, 9) and np.all(np.isfinite(obs))
+    v = np.concatenate(vals)
+    assert abs(v.mean() - 1.0) <= 5 * v.std() / np.sqrt(len(v)) + 0.02
+    assert accs > 0.5 * len(v)
+    cb.trajectory(1, 1e-9); pi = cb.get_momentum(); cb.commit(np.ones(B, int))
+    x = np.concatenate([pi.real.ravel(), pi.imag.ravel()])
+    assert abs(x.mean()) < 0.1 and abs(x.var() - 2.0) < 0.2      # Re, Im ~ N(0, m = 2)
+    cb.close()
