@@ -2,6 +2,7 @@
 // operator it stands in for; the batched trajectory is hmc_sweep! (/root/reference src/HMC.jl:71-144)
 // for B chains at once.  No CPU fallback: every call needs the CUDA device of its handle.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -108,6 +109,10 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   dwhmc_handle_s* hs = new dwhmc_handle_s();
   Handle* h = hs;
   h->device = device; h->B = B; h->Lx = Lx; h->Ly = Ly; h->N = N; h->n = n;
+  if (const char* eg = getenv("DWHMC_NGROUP")) {
+    const int v = atoi(eg);
+    if (v >= 1 && v <= DW_NGROUP) h->ngroups = v;
+  }
   auto fail = [&](int rc) { g_create_err = h->err; dwhmc_destroy(hs); return rc; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DWHMC_E_CUDA); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
@@ -115,8 +120,14 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   cudaEventCreate(&h->ev1);
   cudaEventCreate(&h->ev_begin);
   cudaEventCreate(&h->ev_end);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int g = 0; g < DW_NGROUP; ++g) {
+    cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming);
+  }
   const size_t nB = (size_t)n * B, nnB = (size_t)n * n * B;
   h->nblk = (n - 1 + DW_NB - 1) / DW_NB;
+  h->nbt = (n - 1 + DW_NBT - 1) / DW_NBT;
   h->fchunks = (n + DW_FCHUNK - 1) / DW_FCHUNK;
   h->h_par.assign(6 * (size_t)B, 0.0);
   int rc = DWHMC_OK;
@@ -132,9 +143,9 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   AL(h->obs_dev, (size_t)DWHMC_NOBS * B);
   AL(h->Ppart, (size_t)h->fchunks * nB); AL(h->hpart, (size_t)h->fchunks * B); AL(h->Pbond, nB);
   AL(h->A, nnB); AL(h->V, nnB);
-  AL(h->ypart, (size_t)DW_NSPLIT * nB); AL(h->P1, (size_t)DW_NB * B); AL(h->P2, nB * DW_NB);
-  AL(h->Tf, (size_t)h->nblk * DW_NB * DW_NB * B); AL(h->tau, nB); AL(h->d, nB); AL(h->e, nB);
-  AL(h->Wbt, (size_t)DW_NB * nB); AL(h->Wbt2, (size_t)DW_NB * nB);
+  AL(h->ypart, (size_t)((n + 63) / 64) * nB); AL(h->P1, (size_t)DW_CC * DW_NB * B); AL(h->P2, (size_t)DW_CC * DW_NB * B);
+  AL(h->Tf, (size_t)h->nbt * DW_NBT * DW_NBT * B); AL(h->Gb, (size_t)h->nbt * DW_NBT * DW_NBT * B); AL(h->tau, nB); AL(h->d, nB); AL(h->e, nB);
+  AL(h->Wbt, (size_t)DW_NBT * nB); AL(h->Wbt2, (size_t)DW_NBT * nB);
   AL(h->Z0, nnB); AL(h->Z1, nnB); AL(h->S, nnB);
   AL(h->perm, nB); AL(h->ord, nB);
   AL(h->zvec, nB); AL(h->dl, nB); AL(h->wv, nB); AL(h->dnew, nB); AL(h->zhat, nB); AL(h->stau, nB);
@@ -187,6 +198,11 @@ int dwhmc_destroy(dwhmc_handle hh) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
   if (h->ev_end) cudaEventDestroy(h->ev_end);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int g = 0; g < DW_NGROUP; ++g) {
+    if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
+    if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete static_cast<dwhmc_handle_s*>(hh);
   return DWHMC_OK;
@@ -476,7 +492,7 @@ int dwhmc_reset_timers(dwhmc_handle hh) {
 }
 int dwhmc_set_profiling(dwhmc_handle hh, int on) {
   H_ENTER(hh);
-  h->profiling = on != 0;
+  h->profiling = on < 0 ? 0 : on;
   return DWHMC_OK;
 }
 

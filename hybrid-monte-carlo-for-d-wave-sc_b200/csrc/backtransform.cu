@@ -1,40 +1,110 @@
 // backtransform.cu -- eigenvectors of the BdG matrix from those of the tridiagonal matrix:
 // U <- Q U with Q = H_0 ... H_{n-2} (third stage of diagonalize_H_BdG!,
 // /root/reference src/Hamiltonian.jl:96-114).  The reflectors are grouped into blocks of DW_NB,
-// Q_k = I - V_k T_k V_k^H (T_k from hetrd.cu), applied last block first as three batched
+// Q_k = I - V_k T_k V_k^H of DW_NBT reflectors (T_k from the Gram matrix V_k^H V_k), applied last
+// block first as three batched
 // complex GEMMs on the FP64 tensor cores:  W1 = V_k^H U ; W2 = T_k W1 ; U -= V_k W2.
 #include "dwhmc.h"
 #include "internal.h"
 
+namespace {
+
+__device__ __forceinline__ void cfma_(cplx& acc, cplx a, cplx b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
+// T factor of one block reflector from its Gram matrix G = V^H V (forward, columnwise):
+// T[i,i] = tau_i, T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i].  Thread r owns row r of T, which only
+// depends on earlier entries of the same row, so the recurrence needs no barrier.
+__global__ void __launch_bounds__(DW_NBT) bt_larft_kernel(const cplx* __restrict__ tau, const cplx* __restrict__ Gall,
+                                                          cplx* __restrict__ Tall, int n, int nbt, Mask mask) {
+  const int k = blockIdx.x, b = blockIdx.y;
+  if (!mask.on(b)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);          // [NBT][NBT + 1] row r at T + r * (NBT + 1)
+  cplx* G = T + DW_NBT * (DW_NBT + 1);                   // [NBT][NBT] column-major
+  const int r = threadIdx.x;
+  const int j0 = k * DW_NBT;
+  const int pn = min(DW_NBT, n - 1 - j0);
+  const cplx* Gk = Gall + ((size_t)b * nbt + k) * DW_NBT * DW_NBT;
+  for (int c = 0; c < DW_NBT; ++c) {
+    G[c * DW_NBT + r] = Gk[c * DW_NBT + r];
+    T[r * (DW_NBT + 1) + c] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  cplx* Tr = T + r * (DW_NBT + 1);
+  for (int i = 0; i < pn; ++i) {
+    const cplx t = tau[(size_t)b * n + j0 + i];
+    if (r < i) {
+      cplx s = make_double2(0.0, 0.0);
+      for (int l = r; l < i; ++l) cfma_(s, Tr[l], G[i * DW_NBT + l]);
+      Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
+    } else if (r == i) {
+      Tr[i] = t;
+    }
+  }
+  __syncthreads();
+  cplx* out = Tall + ((size_t)b * nbt + k) * DW_NBT * DW_NBT;
+  for (int c = 0; c < DW_NBT; ++c) out[c * DW_NBT + r] = Tr[c];
+}
+
+}  // namespace
+
 int dw_backtransform(Handle* h, cplx* U, Mask mask) {
-  const int n = h->n, B = h->B;
-  for (int k = h->nblk - 1; k >= 0; --k) {
-    const int j0 = k * DW_NB;
-    const int pn = (n - 1 - j0 < DW_NB) ? n - 1 - j0 : DW_NB;
+  const int n = h->n, B = h->B, nbt = h->nbt;
+  const long long sT = (long long)nbt * DW_NBT * DW_NBT;
+  ZgemmArgs a;
+  a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
+  // Gram matrices of all blocks, then their T factors
+  for (int k = 0; k < nbt; ++k) {
+    const int j0 = k * DW_NBT;
+    const int pn = (n - 1 - j0 < DW_NBT) ? n - 1 - j0 : DW_NBT;
+    const int mk = n - (j0 + 1);
+    const cplx* Vk = h->V + (size_t)j0 * n + (j0 + 1);
+    a.M = pn; a.N = pn; a.K = mk;
+    a.A[0] = Vk; a.lda = n; a.sA = (long long)n * n; a.opA = 1;
+    a.Bm[0] = Vk; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
+    a.C = h->Gb + (size_t)k * DW_NBT * DW_NBT; a.ldc = DW_NBT; a.sC = sT;
+    a.alpha = 1.0; a.beta = 0.0;
+    DW_TRY(dw_zgemm(h, a));
+  }
+  {
+    static bool attr_set[64] = {false};
+    const size_t smem = sizeof(cplx) * (DW_NBT * (DW_NBT + 1) + DW_NBT * DW_NBT);
+    if (!attr_set[h->device & 63]) {
+      DW_CUDA(h, cudaFuncSetAttribute(bt_larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set[h->device & 63] = true;
+    }
+    dim3 grid(nbt, B);
+    bt_larft_kernel<<<grid, DW_NBT, smem, h->stream>>>(h->tau, h->Gb, h->Tf, n, nbt, mask);
+    DW_LAUNCH_CHECK(h);
+  }
+  for (int k = nbt - 1; k >= 0; --k) {
+    const int j0 = k * DW_NBT;
+    const int pn = (n - 1 - j0 < DW_NBT) ? n - 1 - j0 : DW_NBT;
     const int mk = n - (j0 + 1);
     if (pn <= 0 || mk <= 0) continue;
     const cplx* Vk = h->V + (size_t)j0 * n + (j0 + 1);   // rows j0+1.., columns j0..j0+pn-1
     cplx* Uk = U + (j0 + 1);                             // rows j0+1.. of every column
-    ZgemmArgs a;
-    a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
     // W1 (pn x n) = V_k^H U_k
     a.M = pn; a.N = n; a.K = mk;
     a.A[0] = Vk; a.lda = n; a.sA = (long long)n * n; a.opA = 1;
     a.Bm[0] = Uk; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
-    a.C = h->Wbt; a.ldc = DW_NB; a.sC = (long long)DW_NB * n;
+    a.C = h->Wbt; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
     a.alpha = 1.0; a.beta = 0.0;
     DW_TRY(dw_zgemm(h, a));
     // W2 (pn x n) = T_k W1
     a.M = pn; a.N = n; a.K = pn;
-    a.A[0] = h->Tf + (size_t)k * DW_NB * DW_NB; a.lda = DW_NB; a.sA = (long long)h->nblk * DW_NB * DW_NB; a.opA = 0;
-    a.Bm[0] = h->Wbt; a.ldb = DW_NB; a.sB = (long long)DW_NB * n; a.opB = 0;
-    a.C = h->Wbt2; a.ldc = DW_NB; a.sC = (long long)DW_NB * n;
+    a.A[0] = h->Tf + (size_t)k * DW_NBT * DW_NBT; a.lda = DW_NBT; a.sA = sT; a.opA = 0;
+    a.Bm[0] = h->Wbt; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
+    a.C = h->Wbt2; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
     a.alpha = 1.0; a.beta = 0.0;
     DW_TRY(dw_zgemm(h, a));
     // U_k -= V_k W2
     a.M = mk; a.N = n; a.K = pn;
     a.A[0] = Vk; a.lda = n; a.sA = (long long)n * n; a.opA = 0;
-    a.Bm[0] = h->Wbt2; a.ldb = DW_NB; a.sB = (long long)DW_NB * n; a.opB = 0;
+    a.Bm[0] = h->Wbt2; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
     a.C = Uk; a.ldc = n; a.sC = (long long)n * n;
     a.alpha = -1.0; a.beta = 1.0;
     DW_TRY(dw_zgemm(h, a));

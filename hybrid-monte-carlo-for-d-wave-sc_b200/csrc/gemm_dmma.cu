@@ -31,6 +31,7 @@ struct KArgs {
   cplx* C;
   double alpha, beta;
   int lower;
+  int b0;
   Mask mask;
 };
 
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(NTHREADS) zgemm_dmma_kernel(KArgs g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* smem = reinterpret_cast<cplx*>(smem_raw);
 
-  const int b = blockIdx.z;
+  const int b = g.b0 + blockIdx.z;
   if (!g.mask.on(b)) return;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (g.lower && n0 > m0 + BM - 1) return;
@@ -201,9 +202,9 @@ int launch(Handle* h, const ZgemmArgs& a) {
   g.B0 = a.Bm[0]; g.B1 = a.nseg > 1 ? a.Bm[1] : nullptr;
   g.lda = a.lda; g.ldb = a.ldb; g.ldc = a.ldc;
   g.sA = a.sA; g.sB = a.sB; g.sC = a.sC;
-  g.C = a.C; g.alpha = a.alpha; g.beta = a.beta; g.lower = a.lower; g.mask = a.mask;
+  g.C = a.C; g.alpha = a.alpha; g.beta = a.beta; g.lower = a.lower; g.mask = a.mask; g.b0 = a.b0;
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
-  kern<<<grid, NTHREADS, T::SMEM, h->stream>>>(g);
+  kern<<<grid, NTHREADS, T::SMEM, a.stream ? a.stream : h->stream>>>(g);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }

@@ -6,17 +6,21 @@
 // Panels of DW_NB columns.  Inside a panel the trailing matrix is not updated; each column costs
 //   colstep  (one CTA per chain)  finish w_{j-1}; update column j with the panel's V/W; reflector;
 //                                 the small products W^H v, V^H v
-//   hemv     (row blocks x column splits x chains)  y = A[j+1:, j+1:] v   -- HBM-bound, 16 m^2 bytes
+//   hemv     (lower-triangle 64x64 tiles x chains)  y = A[j+1:, j+1:] v   -- HBM-bound, 8 m^2 bytes
 // and each panel ends with the rank-2k update A -= V W^H + W V^H on the FP64 tensor cores
 // (gemm_dmma.cu).  The formulas are the ones prototyped and checked against LAPACK in
 // tests/algo_proto.py.
+#include <cooperative_groups.h>
+
 #include "dwhmc.h"
 #include "internal.h"
 
+namespace cg = cooperative_groups;
+
 namespace {
 
-constexpr int CT = 512;     // threads of the column-step kernel
-constexpr int HT = 128;     // threads (= rows) of a hemv CTA
+constexpr int CC = DW_CC;    // CTAs per cluster (= per chain) of the column-step kernel
+constexpr int CT = 256;     // threads per CTA of the column-step kernel
 
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -60,85 +64,122 @@ __device__ __forceinline__ cplx block_sum(cplx v, cplx* red) {
 struct ColArgs {
   cplx* A; cplx* V; cplx* W; cplx* ypart; cplx* P1; cplx* P2; cplx* tau;
   double* d; double* e;
-  int n, B, j, j0, finish_prev, make_ref;
+  int n, B, b0, j, j0, finish_prev, make_ref;
   Mask mask;
 };
 
-__global__ void __launch_bounds__(CT) colstep_kernel(ColArgs g) {
-  const int b = blockIdx.x;
-  if (!g.mask.on(b)) return;
+// Column step of the panel factorisation: a cluster of CC CTAs per chain, each owning a contiguous
+// slice of the rows j..n-1.  Block sums are exchanged through distributed shared memory (one slot
+// array per CTA, read by every CTA of the cluster after a cluster barrier, summed in rank order).
+//   finish_prev:  w_{j-1} = tau (y - V (W^H v) - W (V^H v)),  w -= tau/2 (w^H v) v
+//   make_ref:     a = A[j:, j] - V conj(W[j,:]) - W conj(V[j,:]);  reflector v_j, tau_j, e_j, d_j;
+//                 partial products W^H v_j, V^H v_j of this CTA's rows (summed by the next launch)
+__global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(ColArgs g) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = g.b0 + blockIdx.x / CC;
+  if (!g.mask.on(b)) return;          // the whole cluster leaves together
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* sv = reinterpret_cast<cplx*>(smem_raw);   // [n] reflector
-  cplx* sw = sv + g.n;                            // [n] w, then the updated column a
-  cplx* rowW = sw + g.n;                          // [NB]
+  const int n = g.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = g.j, j0 = g.j0;
+  const int chunk = (n - j + CC - 1) / CC;          // rows j..n-1 in CC slices
+  const int chunk_max = (n + CC - 1) / CC;
+  cplx* sv = reinterpret_cast<cplx*>(smem_raw);   // [chunk_max] reflector rows of this CTA
+  cplx* sw = sv + chunk_max;                      // [chunk_max] w, then the updated column a
+  cplx* rowW = sw + chunk_max;                    // [NB]
   cplx* rowV = rowW + DW_NB;                      // [NB]
   cplx* red = rowV + DW_NB;                       // [32]
+  __shared__ cplx xch[8];                         // DSMEM exchange: 0 dot, 1 norm, 2 a[j], 3 a[j+1], 4 w[j]
   __shared__ cplx s_scale;
-
-  const int n = g.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lo = j + rank * chunk, hi = min(n, lo + chunk);
   const size_t mat = (size_t)b * n * n;
   cplx* A = g.A + mat;
   cplx* V = g.V + mat;
   cplx* W = g.W + mat;
-  const int j0 = g.j0;
 
   if (g.finish_prev) {
-    // ---- finish w for column jp = j - 1
-    const int jp = g.j - 1, ip = jp - j0;
+    const int jp = j - 1, ip = jp - j0;
     if (tid < ip) {
-      rowW[tid] = g.P1[(size_t)b * DW_NB + tid];                   // W_panel^H v
-      rowV[tid] = g.P2[((size_t)b * n + jp) * DW_NB + tid];        // V_panel^H v
+      cplx p1 = make_double2(0.0, 0.0), p2 = p1;
+      for (int c = 0; c < CC; ++c) {
+        p1 = cadd(p1, g.P1[((size_t)b * CC + c) * DW_NB + tid]);     // W_panel^H v
+        p2 = cadd(p2, g.P2[((size_t)b * CC + c) * DW_NB + tid]);     // V_panel^H v
+      }
+      rowW[tid] = p1;
+      rowV[tid] = p2;
     }
     const cplx tau = g.tau[(size_t)b * n + jp];
+    const int nslots = (n - jp - 1 + 63) / 64;     // tiles per dimension of the hemv of column jp
     __syncthreads();
     cplx dot = make_double2(0.0, 0.0);
-    for (int r = jp + 1 + tid; r < n; r += CT) {
+    for (int r = lo + tid; r < hi; r += CT) {
       cplx acc = make_double2(0.0, 0.0);
-#pragma unroll
-      for (int s = 0; s < DW_NSPLIT; ++s) acc = cadd(acc, g.ypart[((size_t)s * g.B + b) * n + r]);
+      for (int s = 0; s < nslots; ++s) acc = cadd(acc, g.ypart[((size_t)s * g.B + b) * n + r]);
       for (int k = 0; k < ip; ++k) {
         cfms(acc, V[(size_t)(j0 + k) * n + r], rowW[k]);
         cfms(acc, W[(size_t)(j0 + k) * n + r], rowV[k]);
       }
       const cplx wv = cmul(tau, acc);
       const cplx vv = V[(size_t)jp * n + r];
-      sw[r] = wv;
-      sv[r] = vv;
+      sw[r - lo] = wv;
+      sv[r - lo] = vv;
       cfmac(dot, wv, vv);
     }
     dot = block_sum(dot, red);
+    if (tid == 0) xch[0] = dot;
+    cluster.sync();
+    dot = make_double2(0.0, 0.0);
+    for (int c = 0; c < CC; ++c) dot = cadd(dot, cluster.map_shared_rank(xch, c)[0]);
     cplx alpha = cmul(tau, dot);
     alpha.x *= -0.5; alpha.y *= -0.5;
-    for (int r = jp + 1 + tid; r < n; r += CT) {
-      cplx wv = sw[r];
-      cfma(wv, alpha, sv[r]);
+    for (int r = lo + tid; r < hi; r += CT) {
+      cplx wv = sw[r - lo];
+      cfma(wv, alpha, sv[r - lo]);
       W[(size_t)jp * n + r] = wv;
+      if (r == j) xch[4] = wv;
     }
-    __syncthreads();
+    if (!g.make_ref) {
+      cluster.sync();       // nobody may exit while its exchange slots can still be read
+      return;
+    }
   }
 
-  if (g.make_ref) {
-    const int j = g.j, i = j - j0;
+  {
+    const int i = j - j0;
+    cluster.sync();         // W[:, j-1] complete; xch[4] of rank 0 valid
     if (tid < i) {
-      const cplx a = W[(size_t)(j0 + tid) * n + j], c = V[(size_t)(j0 + tid) * n + j];
+      cplx a, c;
+      if (g.finish_prev && tid == i - 1) {
+        a = cluster.map_shared_rank(xch, 0)[4];          // W[j, j-1], owned by rank 0
+        c = make_double2(1.0, 0.0);                      // V[j, j-1] is the unit entry
+      } else {
+        a = W[(size_t)(j0 + tid) * n + j];
+        c = V[(size_t)(j0 + tid) * n + j];
+      }
       rowW[tid] = make_double2(a.x, -a.y);
       rowV[tid] = make_double2(c.x, -c.y);
     }
     __syncthreads();
     cplx nrm = make_double2(0.0, 0.0);
-    for (int r = j + tid; r < n; r += CT) {
+    for (int r = lo + tid; r < hi; r += CT) {
       cplx a = A[(size_t)j * n + r];
       for (int k = 0; k < i; ++k) {
         cfms(a, V[(size_t)(j0 + k) * n + r], rowW[k]);
         cfms(a, W[(size_t)(j0 + k) * n + r], rowV[k]);
       }
-      sw[r] = a;
+      sw[r - lo] = a;
       if (r >= j + 2) nrm.x += a.x * a.x + a.y * a.y;
+      if (r == j) xch[2] = a;
+      if (r == j + 1) xch[3] = a;
     }
-    nrm = block_sum(nrm, red);   // also orders the sw writes before the reads below
+    nrm = block_sum(nrm, red);
+    if (tid == 0) xch[1] = nrm;
+    cluster.sync();
     if (tid == 0) {
-      const cplx a0 = sw[j], alpha = sw[j + 1];
-      const double xn2 = nrm.x;
+      double xn2 = 0.0;
+      for (int c = 0; c < CC; ++c) xn2 += cluster.map_shared_rank(xch, c)[1].x;
+      const cplx a0 = cluster.map_shared_rank(xch, 0)[2];
+      const cplx alpha = cluster.map_shared_rank(xch, 1 / chunk)[3];   // rank owning row j + 1
       double beta;
       cplx tau, scale;
       if (xn2 == 0.0 && alpha.y == 0.0) {
@@ -148,106 +189,130 @@ __global__ void __launch_bounds__(CT) colstep_kernel(ColArgs g) {
       } else {
         beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + xn2), alpha.x);
         tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-        // scale = 1 / (alpha - beta)
-        const double dr = alpha.x - beta, di = alpha.y;
+        const double dr = alpha.x - beta, di = alpha.y;     // scale = 1 / (alpha - beta)
         const double den = dr * dr + di * di;
         scale = make_double2(dr / den, -di / den);
       }
-      g.d[(size_t)b * n + j] = a0.x;
-      g.e[(size_t)b * n + j] = beta;
-      g.tau[(size_t)b * n + j] = tau;
+      if (rank == 0) {
+        g.d[(size_t)b * n + j] = a0.x;
+        g.e[(size_t)b * n + j] = beta;
+        g.tau[(size_t)b * n + j] = tau;
+      }
       s_scale = scale;
     }
     __syncthreads();
     const cplx scale = s_scale;
-    for (int r = j + 1 + tid; r < n; r += CT) {
-      const cplx v = (r == j + 1) ? make_double2(1.0, 0.0) : cmul(sw[r], scale);
-      sv[r] = v;
+    for (int r = max(lo, j + 1) + tid; r < hi; r += CT) {
+      const cplx v = (r == j + 1) ? make_double2(1.0, 0.0) : cmul(sw[r - lo], scale);
+      sv[r - lo] = v;
       V[(size_t)j * n + r] = v;
     }
     __syncthreads();
-    // small products: P1[k] = W[:, j0+k]^H v, P2[k] = V[:, j0+k]^H v  (k < i), one warp per product
+    // partial products over this CTA's rows: P1[k] = W[:, j0+k]^H v, P2[k] = V[:, j0+k]^H v (k < i)
     const int nw = CT / 32;
+    const int r0 = max(lo, j + 1);
     for (int q = warp; q < 2 * i; q += nw) {
       const int k = q >> 1, which = q & 1;
       const cplx* src = (which ? V : W) + (size_t)(j0 + k) * n;
       cplx acc = make_double2(0.0, 0.0);
-      for (int r = j + 1 + lane; r < n; r += 32) cfmac(acc, src[r], sv[r]);
+      for (int r = r0 + lane; r < hi; r += 32) cfmac(acc, src[r], sv[r - lo]);
       acc = warp_sum(acc);
       if (lane == 0) {
-        if (which) g.P2[((size_t)b * n + j) * DW_NB + k] = acc;
-        else g.P1[(size_t)b * DW_NB + k] = acc;
+        if (which) g.P2[((size_t)b * CC + rank) * DW_NB + k] = acc;
+        else g.P1[((size_t)b * CC + rank) * DW_NB + k] = acc;
       }
     }
+    cluster.sync();         // exchange slots stay alive until every CTA has read them
   }
 }
 
-// y = A[q0:, q0:] v for the column split blockIdx.y; q0 = j + 1
-__global__ void __launch_bounds__(HT) hemv_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
-                                                  cplx* __restrict__ ypart, int n, int B, int j, Mask mask) {
-  const int b = blockIdx.z;
+// y = A[q0:, q0:] v reading only the lower triangle (q0 = j + 1).  One CTA per 64x64 tile (I >= J) of
+// the trailing block: the tile is staged once in shared memory (cp.async, 16 B) and used twice, for
+// y[rows of I] += T v[cols of J] and y[rows of J] += T^H v[rows of I].  Partial results go to slot J
+// (row pass) / slot I (column pass) of ypart, so every row of block X receives exactly one
+// contribution in each slot 0..nt-1 and the reduction in colstep_kernel has a fixed order.
+constexpr int TS = 64;
+constexpr int TLD = TS + 1;   // padded: the column pass reads with stride TLD, conflict-free
+constexpr size_t HEMV_SMEM = sizeof(cplx) * (TS * TLD + 2 * TS + 8 * TS);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+
+__global__ void __launch_bounds__(256) hemv_lower_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
+                                                         cplx* __restrict__ ypart, int n, int B, int b0, int j,
+                                                         Mask mask) {
+  const int b = b0 + blockIdx.y;
   if (!mask.on(b)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* sv = reinterpret_cast<cplx*>(smem_raw);
+  cplx* As = reinterpret_cast<cplx*>(smem_raw);   // [TS][TLD], column-major tile
+  cplx* vr = As + TS * TLD;                       // v on the tile's rows
+  cplx* vc = vr + TS;                             // v on the tile's columns
+  cplx* red = vc + TS;                            // [2][4][TS]
   const int q0 = j + 1, m = n - q0;
-  const int cs = (m + DW_NSPLIT - 1) / DW_NSPLIT;
-  const int s = blockIdx.y;
-  const int c_lo = s * cs, c_hi = min(m, c_lo + cs);
+  // tile (I, J), I >= J, from the linear index t = I (I + 1) / 2 + J
+  const int t = blockIdx.x;
+  int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((I + 1) * (I + 2) / 2 <= t) ++I;
+  while (I * (I + 1) / 2 > t) --I;
+  const int J = t - I * (I + 1) / 2;
+  const int R0 = I * TS, C0 = J * TS;
+  const int tid = threadIdx.x;
   const size_t mat = (size_t)b * n * n;
+  const cplx* A = Aall + mat + (size_t)(q0 + C0) * n + q0 + R0;
   const cplx* v = Vall + mat + (size_t)j * n + q0;
-  for (int c = c_lo + threadIdx.x; c < c_hi; c += HT) sv[c - c_lo] = v[c];
-  __syncthreads();
-  const int rl = blockIdx.x * HT + threadIdx.x;
-  if (rl >= m) return;
-  const cplx* Ar = Aall + mat + (size_t)q0 * n + q0 + rl;   // A[q0 + rl, q0 + c] = Ar[c * n]
-  cplx a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
-  int c = c_lo;
-  for (; c + 4 <= c_hi; c += 4) {
-    const cplx x0 = Ar[(size_t)c * n], x1 = Ar[(size_t)(c + 1) * n];
-    const cplx x2 = Ar[(size_t)(c + 2) * n], x3 = Ar[(size_t)(c + 3) * n];
-    cfma(a0, x0, sv[c - c_lo]);
-    cfma(a1, x1, sv[c + 1 - c_lo]);
-    cfma(a2, x2, sv[c + 2 - c_lo]);
-    cfma(a3, x3, sv[c + 3 - c_lo]);
+#pragma unroll
+  for (int it = 0; it < (TS * TS) / 256; ++it) {
+    const int idx = tid + it * 256;
+    const int r = idx & (TS - 1), c = idx >> 6;
+    const bool p = (R0 + r < m) && (C0 + c < m);
+    cp_async16(As + c * TLD + r, p ? A + (size_t)c * n + r : A, p);
   }
-  for (; c < c_hi; ++c) cfma(a0, Ar[(size_t)c * n], sv[c - c_lo]);
-  a0 = cadd(cadd(a0, a1), cadd(a2, a3));
-  ypart[((size_t)s * B + b) * n + q0 + rl] = a0;
+  asm volatile("cp.async.commit_group;\n" ::);
+  if (tid < TS) vr[tid] = (R0 + tid < m) ? v[R0 + tid] : make_double2(0.0, 0.0);
+  else if (tid < 2 * TS) vc[tid - TS] = (C0 + tid - TS < m) ? v[C0 + tid - TS] : make_double2(0.0, 0.0);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  const int x = tid & (TS - 1), q = tid >> 6;     // x: row (row pass) / column (column pass); q: 16-wide group
+  const bool diag = (I == J);
+  cplx acc = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
+#pragma unroll 4
+  for (int cc = 0; cc < 16; ++cc) {
+    const int c = q * 16 + cc;
+    if (!diag || c <= x) cfma(acc, As[c * TLD + x], vc[c]);
+  }
+#pragma unroll 4
+  for (int rr = 0; rr < 16; ++rr) {
+    const int r = q * 16 + rr;
+    if (!diag || r > x) cfmac(acc2, As[x * TLD + r], vr[r]);
+  }
+  red[q * TS + x] = acc;
+  red[(4 + q) * TS + x] = acc2;
+  __syncthreads();
+  if (tid < 2 * TS) {
+    const int which = tid >> 6, xx = tid & (TS - 1);
+    const cplx* rp = red + which * 4 * TS + xx;
+    cplx sum = cadd(cadd(rp[0], rp[TS]), cadd(rp[2 * TS], rp[3 * TS]));
+    if (diag) {
+      if (which == 0) {
+        const cplx* rq = red + 4 * TS + xx;
+        sum = cadd(sum, cadd(cadd(rq[0], rq[TS]), cadd(rq[2 * TS], rq[3 * TS])));
+        if (R0 + xx < m) ypart[((size_t)I * B + b) * n + q0 + R0 + xx] = sum;
+      }
+    } else if (which == 0) {
+      if (R0 + xx < m) ypart[((size_t)J * B + b) * n + q0 + R0 + xx] = sum;
+    } else {
+      if (C0 + xx < m) ypart[((size_t)I * B + b) * n + q0 + C0 + xx] = sum;
+    }
+  }
 }
 
 __global__ void lastd_kernel(const cplx* __restrict__ A, double* __restrict__ d, int n, int B, Mask mask) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B || !mask.on(b)) return;
   d[(size_t)b * n + n - 1] = A[(size_t)b * n * n + (size_t)(n - 1) * n + (n - 1)].x;
-}
-
-// T factors of the block reflectors (forward, columnwise): T[i,i] = tau_i,
-// T[0:i, i] = -tau_i T[0:i,0:i] (V^H v_i); one warp per (block, chain)
-__global__ void __launch_bounds__(32) larft_kernel(const cplx* __restrict__ tau, const cplx* __restrict__ P2,
-                                                   cplx* __restrict__ Tf, int n, int nblk, Mask mask) {
-  const int k = blockIdx.x, b = blockIdx.y;
-  if (!mask.on(b)) return;
-  __shared__ cplx T[DW_NB][DW_NB + 1];
-  const int lane = threadIdx.x;
-  const int j0 = k * DW_NB;
-  const int pn = min(DW_NB, n - 1 - j0);
-  for (int c = 0; c < DW_NB; ++c) T[lane][c] = make_double2(0.0, 0.0);
-  __syncwarp();
-  for (int i = 0; i < pn; ++i) {
-    const cplx t = tau[(size_t)b * n + j0 + i];
-    if (lane < i) {
-      const cplx* p = P2 + ((size_t)b * n + j0 + i) * DW_NB;
-      cplx s = make_double2(0.0, 0.0);
-      for (int l = lane; l < i; ++l) cfma(s, T[lane][l], p[l]);
-      cplx r = cmul(t, s);
-      T[lane][i] = make_double2(-r.x, -r.y);
-    } else if (lane == i) {
-      T[lane][i] = t;
-    }
-    __syncwarp();
-  }
-  cplx* out = Tf + ((size_t)b * nblk + k) * DW_NB * DW_NB;
-  for (int c = 0; c < DW_NB; ++c) out[c * DW_NB + lane] = T[lane][c];
 }
 
 }  // namespace
@@ -259,57 +324,80 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
     DW_LAUNCH_CHECK(h);
     return DWHMC_OK;
   }
-  const size_t col_smem = sizeof(cplx) * (2 * (size_t)n + 2 * DW_NB + 32);
+  const size_t col_smem = sizeof(cplx) * (2 * (size_t)((n + CC - 1) / CC) + 2 * DW_NB + 32);
   static bool attr_set[64] = {false};
   if (!attr_set[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(colstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DW_CUDA(h, cudaFuncSetAttribute(hemv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEMV_SMEM));
     attr_set[h->device & 63] = true;
   }
   if (col_smem > 200 * 1024) { h->err = "dw_hetrd: matrix too large for the column-step kernel"; return DWHMC_E_BADARG; }
-  ColArgs g;
-  g.A = h->A; g.V = h->V; g.W = W; g.ypart = h->ypart; g.P1 = h->P1; g.P2 = h->P2; g.tau = h->tau;
-  g.d = h->d; g.e = h->e; g.n = n; g.B = B; g.mask = mask;
+  // The batch is split into groups that run on their own streams: the latency-bound column step of
+  // one group (one CTA per chain) overlaps the HBM-bound hemv of the other.
+  const int G = (B >= 2 * h->ngroups && n >= 256 && h->profiling < 2) ? h->ngroups : 1;
+  cudaStream_t st[DW_NGROUP];
+  int gb0[DW_NGROUP], gB[DW_NGROUP];
+  for (int g = 0; g < G; ++g) {
+    gb0[g] = (int)((long long)B * g / G);
+    gB[g] = (int)((long long)B * (g + 1) / G) - gb0[g];
+    st[g] = (G == 1) ? h->stream : h->gstream[g];
+  }
+  if (G > 1) {
+    DW_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    for (int g = 0; g < G; ++g) DW_CUDA(h, cudaStreamWaitEvent(st[g], h->ev_fork, 0));
+  }
+  ColArgs ca;
+  ca.A = h->A; ca.V = h->V; ca.W = W; ca.ypart = h->ypart; ca.P1 = h->P1; ca.P2 = h->P2; ca.tau = h->tau;
+  ca.d = h->d; ca.e = h->e; ca.n = n; ca.B = B; ca.mask = mask;
   for (int j0 = 0; j0 < n - 1; j0 += DW_NB) {
     const int pn = (n - 1 - j0 < DW_NB) ? n - 1 - j0 : DW_NB;
-    g.j0 = j0;
+    ca.j0 = j0;
     for (int i = 0; i < pn; ++i) {
       const int j = j0 + i;
-      g.j = j; g.finish_prev = (i > 0); g.make_ref = 1;
-      colstep_kernel<<<B, CT, col_smem, h->stream>>>(g);
-      DW_LAUNCH_CHECK(h);
       const int m = n - j - 1;
-      const int cs = (m + DW_NSPLIT - 1) / DW_NSPLIT;
-      dim3 grid((m + HT - 1) / HT, DW_NSPLIT, B);
-      if (h->profiling) cudaEventRecord(h->ev_begin, h->stream);
-      hemv_kernel<<<grid, HT, sizeof(cplx) * cs, h->stream>>>(h->A, h->V, h->ypart, n, B, j, mask);
-      DW_LAUNCH_CHECK(h);
-      if (h->profiling) {
-        cudaEventRecord(h->ev_end, h->stream);
-        cudaEventSynchronize(h->ev_end);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
-        h->timers[7] += ms;
+      const int nt = (m + TS - 1) / TS;
+      for (int g = 0; g < G; ++g) {
+        ca.j = j; ca.finish_prev = (i > 0); ca.make_ref = 1; ca.b0 = gb0[g];
+        colstep_kernel<<<gB[g] * CC, CT, col_smem, st[g]>>>(ca);
+        DW_LAUNCH_CHECK(h);
+        dim3 grid(nt * (nt + 1) / 2, gB[g]);
+        if (h->profiling >= 2) cudaEventRecord(h->ev_begin, st[g]);
+        hemv_lower_kernel<<<grid, 256, HEMV_SMEM, st[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        DW_LAUNCH_CHECK(h);
+        if (h->profiling >= 2) {
+          cudaEventRecord(h->ev_end, st[g]);
+          cudaEventSynchronize(h->ev_end);
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
+          h->timers[7] += ms;
+        }
       }
     }
     const int j1 = j0 + pn;
-    g.j = j1; g.finish_prev = 1; g.make_ref = 0;
-    colstep_kernel<<<B, CT, col_smem, h->stream>>>(g);
-    DW_LAUNCH_CHECK(h);
-    // trailing update A[j1:, j1:] -= V W^H + W V^H  (rows >= j1 of the panel columns)
-    ZgemmArgs a;
-    a.M = n - j1; a.N = n - j1; a.K = pn; a.nseg = 2;
-    a.A[0] = h->V + (size_t)j0 * n + j1; a.Bm[0] = W + (size_t)j0 * n + j1;
-    a.A[1] = W + (size_t)j0 * n + j1;    a.Bm[1] = h->V + (size_t)j0 * n + j1;
-    a.lda = n; a.ldb = n; a.ldc = n;
-    a.sA = (long long)n * n; a.sB = (long long)n * n; a.sC = (long long)n * n;
-    a.C = h->A + (size_t)j1 * n + j1;
-    a.alpha = -1.0; a.beta = 1.0; a.opA = 0; a.opB = 1; a.lower = 0; a.batch = B; a.mask = mask;
-    DW_TRY(dw_zgemm(h, a));
+    for (int g = 0; g < G; ++g) {
+      ca.j = j1; ca.finish_prev = 1; ca.make_ref = 0; ca.b0 = gb0[g];
+      colstep_kernel<<<gB[g] * CC, CT, col_smem, st[g]>>>(ca);
+      DW_LAUNCH_CHECK(h);
+      // trailing update A[j1:, j1:] -= V W^H + W V^H, lower-triangle tiles only
+      ZgemmArgs a;
+      a.M = n - j1; a.N = n - j1; a.K = pn; a.nseg = 2;
+      a.A[0] = h->V + (size_t)j0 * n + j1; a.Bm[0] = W + (size_t)j0 * n + j1;
+      a.A[1] = W + (size_t)j0 * n + j1;    a.Bm[1] = h->V + (size_t)j0 * n + j1;
+      a.lda = n; a.ldb = n; a.ldc = n;
+      a.sA = (long long)n * n; a.sB = (long long)n * n; a.sC = (long long)n * n;
+      a.C = h->A + (size_t)j1 * n + j1;
+      a.alpha = -1.0; a.beta = 1.0; a.opA = 0; a.opB = 1; a.lower = 1; a.batch = gB[g]; a.mask = mask;
+      a.b0 = gb0[g]; a.stream = st[g];
+      DW_TRY(dw_zgemm(h, a));
+    }
+  }
+  if (G > 1) {
+    for (int g = 0; g < G; ++g) {
+      DW_CUDA(h, cudaEventRecord(h->ev_join[g], st[g]));
+      DW_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[g], 0));
+    }
   }
   lastd_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(h->A, h->d, n, B, mask);
-  DW_LAUNCH_CHECK(h);
-  dim3 tg(h->nblk, B);
-  larft_kernel<<<tg, 32, 0, h->stream>>>(h->tau, h->P2, h->Tf, n, h->nblk, mask);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }

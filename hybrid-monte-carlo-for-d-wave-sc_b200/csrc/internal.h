@@ -9,8 +9,10 @@
 #include "stedc_tree.h"
 
 #define DW_NB 32          // Householder panel width (tridiagonalisation and back-transform blocks)
+#define DW_CC 4           // CTAs per cluster in the column-step kernel
+#define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
 #define DW_LEAF 36        // largest D&C leaf
-#define DW_NSPLIT 4       // column splits of the trailing-matrix hemv
+#define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
 #define DW_FCHUNK 32      // eigenvector columns per CTA in the bond-correlator kernel
 
 typedef double2 cplx;
@@ -37,9 +39,11 @@ struct Handle {
   int B = 0, Lx = 0, Ly = 0, N = 0, n = 0;
   cudaStream_t stream = nullptr;
   std::string err;
-  bool profiling = false;
+  int profiling = 0;             // 1: stage timers; 2: also per-launch hemv timing (serialises the groups)
   double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
+  cudaStream_t gstream[DW_NGROUP] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[DW_NGROUP] = {};
   double last_ms = 0.0;          // device time of the last dwhmc_run_sweeps (events on `stream`)
   std::vector<void*> allocs;    // everything cudaMalloc'ed, for destroy
 
@@ -83,15 +87,16 @@ struct Handle {
   // eigensolver workspace
   cplx* A = nullptr;            // [n*n*B] work matrix (full Hermitian storage)
   cplx* V = nullptr;            // [n*n*B] Householder vectors, explicit unit entries, zeros above
-  cplx* ypart = nullptr;        // [NSPLIT*n*B] hemv partial results
-  cplx* P1 = nullptr;           // [NB*B]   W_panel^H v
-  cplx* P2 = nullptr;           // [n*NB*B] V_panel^H v, kept for the T factors
-  cplx* Tf = nullptr;           // [nblk*NB*NB*B] block reflector T factors
+  cplx* ypart = nullptr;        // [ceil(n/64)*n*B] hemv partial results, one slot per tile row/column
+  cplx* P1 = nullptr;           // [CC*NB*B] W_panel^H v, one partial per cluster rank
+  cplx* P2 = nullptr;           // [CC*NB*B] V_panel^H v
+  cplx* Gb = nullptr;           // [nbt*NBT*NBT*B] Gram matrices of the back-transform blocks
+  cplx* Tf = nullptr;           // [nbt*NBT*NBT*B] block reflector T factors
   cplx* tau = nullptr;          // [n*B]
   double *d = nullptr, *e = nullptr;            // [n*B]
-  cplx* Wbt = nullptr;          // [NB*n*B] back-transform workspace
+  cplx* Wbt = nullptr;          // [NBT*n*B] back-transform workspace
   cplx* Wbt2 = nullptr;
-  int nblk = 0;
+  int nblk = 0, nbt = 0;
   // D&C workspace
   DcTree tree;
   std::vector<DcLevelDev> levels;
@@ -107,6 +112,7 @@ struct Handle {
   int* nrot = nullptr;          // [n*B]
   double* rho = nullptr;        // [n*B]
   int* status = nullptr;        // [4] device: [0] leaf failures, [1] secular non-convergence
+  int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
   long long launches = 0;
   long long eigensolves = 0;
 };
@@ -167,6 +173,8 @@ struct ZgemmArgs {
   int lower;                   // only tiles touching the lower triangle
   int batch;
   Mask mask;
+  int b0 = 0;                  // first chain of the launch (chain groups)
+  cudaStream_t stream = nullptr;   // nullptr = the handle's stream
 };
 int dw_zgemm(Handle* h, const ZgemmArgs& a);
 

@@ -207,8 +207,9 @@ class ChainBatch:
         return nacc, dH, obs
 
     # ---- instrumentation
-    def set_profiling(self, on: bool):
-        check(lib.dwhmc_set_profiling(self._h, int(on)), self._h)
+    def set_profiling(self, level):
+        """0 off; 1 per-stage CUDA-event timers; 2 also times every hemv launch (serialises the chain groups)."""
+        check(lib.dwhmc_set_profiling(self._h, int(level)), self._h)
 
     def reset_timers(self):
         check(lib.dwhmc_reset_timers(self._h), self._h)

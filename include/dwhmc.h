@@ -141,7 +141,9 @@ int dwhmc_reset_timers(dwhmc_handle h);
 /* device time (ms) of the sweeps of the last dwhmc_run_sweeps call, measured with CUDA events
  * recorded on the handle's stream around the enqueued work (excludes the final D2H copies) */
 int dwhmc_last_elapsed_ms(dwhmc_handle h, double* out);
-/* enable (1) / disable (0) per-stage event timing (adds stream synchronisation) */
+/* 0: off; 1: per-stage event timing (adds a stream synchronisation per stage); 2: additionally
+ * time every hemv launch on its own (slot [7]; serialises the chain groups of the
+ * tridiagonalisation, so stage times at level 2 are not representative) */
 int dwhmc_set_profiling(dwhmc_handle h, int on);
 
 /* stage-level entry points used by the parity tests of the eigensolver:
@@ -149,8 +151,8 @@ int dwhmc_set_profiling(dwhmc_handle h, int on);
  * solve a caller-supplied tridiagonal problem (d, e) -> w (double[n*B]), Z (double[n*n*B]). */
 int dwhmc_debug_tridiagonalize(dwhmc_handle h, double* d, double* e);
 int dwhmc_debug_stedc(dwhmc_handle h, const double* d, const double* e, double* w, double* Z);
-/* diagonalise caller-supplied Hermitian matrices (complex[n*n*B], full storage: both
- * triangles are read) -> E (double[n*B]), U (complex[n*n*B]); does not touch Delta, pi,
+/* diagonalise caller-supplied Hermitian matrices (complex[n*n*B], column-major; only the
+ * lower triangle is read) -> E (double[n*B]), U (complex[n*n*B]); does not touch Delta, pi,
  * E_n or U of the chains (it uses the proposal buffers). */
 int dwhmc_debug_heev(dwhmc_handle h, const double* A, double* E, double* U);
 

@@ -30,11 +30,13 @@ print(f"diagonalize: {t1*1e3:.1f} ms for {B} matrices of n={n} -> {t1/B*1e3:.3f}
 E = cb.get_eigenvalues(); U = cb.get_eigenvectors()[0].T
 print("sym err", np.max(np.abs(E + E[:, ::-1])), "orth", np.max(np.abs(U.conj().T @ U - np.eye(n))))
 dt = np.array([dwhmc.calc_optimal_dt(bb, 0.8, 1.0, Nt) for bb in beta])
-cb.set_profiling(True); cb.reset_timers()
+cb.set_profiling(1); cb.reset_timers()
 t0 = time.time(); nacc, dH, _ = cb.run_sweeps(sweeps, Nt, dt); t1 = time.time() - t0
 tm = cb.timers()
 print(f"profiled: {sweeps} sweeps x {B} chains, Nt={Nt}: {t1:.3f} s; timers {tm}")
-cb.set_profiling(False); cb.reset_timers()
+cb.set_profiling(2); cb.reset_timers(); cb.diagonalize_H_BdG()
+print("hemv-only ms per batched solve (serial groups):", cb.timers()["hemv_ms"])
+cb.set_profiling(0); cb.reset_timers()
 t0 = time.time(); nacc, dH, _ = cb.run_sweeps(sweeps, Nt, dt); t1 = time.time() - t0
 print(f"unprofiled: {t1:.3f} s -> {sweeps*B/t1:.2f} traj/s, {sweeps*B*Nt/t1:.1f} eigensolves/s, "
       f"{sweeps*B*Nt*(40/3)*n**3/t1/1e12:.2f} TFLOP/s algorithmic; acc {nacc.mean()/sweeps:.2f}; dH {dH[:4]}")
