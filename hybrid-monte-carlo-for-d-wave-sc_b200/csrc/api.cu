@@ -121,9 +121,16 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   cudaEventCreate(&h->ev_begin);
   cudaEventCreate(&h->ev_end);
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-  for (int g = 0; g < DW_NGROUP; ++g) {
-    cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming);
+  {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
+    for (int g = 0; g < DW_NGROUP; ++g) {
+      cudaStreamCreateWithPriority(&h->gstream[g], cudaStreamNonBlocking, prio_lo);
+      cudaStreamCreateWithPriority(&h->gstream_hi[g], cudaStreamNonBlocking, prio_hi);
+      cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_bulk[g], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&h->ev_col[g], cudaEventDisableTiming);
+    }
   }
   const size_t nB = (size_t)n * B, nnB = (size_t)n * n * B;
   h->nblk = (n - 1 + DW_NB - 1) / DW_NB;
@@ -201,7 +208,10 @@ int dwhmc_destroy(dwhmc_handle hh) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (int g = 0; g < DW_NGROUP; ++g) {
     if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
+    if (h->ev_bulk[g]) cudaEventDestroy(h->ev_bulk[g]);
+    if (h->ev_col[g]) cudaEventDestroy(h->ev_col[g]);
     if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+    if (h->gstream_hi[g]) cudaStreamDestroy(h->gstream_hi[g]);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete static_cast<dwhmc_handle_s*>(hh);

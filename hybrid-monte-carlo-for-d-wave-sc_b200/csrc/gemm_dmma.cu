@@ -109,19 +109,32 @@ __global__ void __launch_bounds__(NTHREADS) zgemm_dmma_kernel(KArgs g) {
     }
   };
 
-  double cr[MI][NI][2], ci[MI][NI][2];
-#pragma unroll
-  for (int i = 0; i < MI; ++i)
-#pragma unroll
-    for (int j = 0; j < NI; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
-
+  const int fr = lane >> 2, fk = lane & 3;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < KT) load_tile(s, s);
     cp_async_commit();
   }
 
-  const int fr = lane >> 2, fk = lane & 3;
+  // The accumulators start from (beta / alpha) * C, so the read of C overlaps the pipeline prologue
+  // instead of stalling the epilogue (alpha = -1, beta = 1 for the rank-k updates: exact).
+  double cr[MI][NI][2], ci[MI][NI][2];
+  {
+    const double scale = (g.beta != 0.0) ? g.beta / g.alpha : 0.0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int row = m0 + wm0 + i * 8 + fr;
+          const int col = n0 + wn0 + j * 8 + 2 * fk + q;
+          cplx old = make_double2(0.0, 0.0);
+          if (g.beta != 0.0 && row < g.M && col < g.N) old = C[(size_t)col * g.ldc + row];
+          cr[i][j][q] = scale * old.x;
+          ci[i][j][q] = scale * old.y;
+        }
+  }
   for (int kt = 0; kt < KT; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
@@ -177,11 +190,6 @@ __global__ void __launch_bounds__(NTHREADS) zgemm_dmma_kernel(KArgs g) {
           cplx out;
           out.x = g.alpha * cr[i][j][q];
           out.y = g.alpha * ci[i][j][q];
-          if (g.beta != 0.0) {
-            cplx old = *p;
-            out.x += g.beta * old.x;
-            out.y += g.beta * old.y;
-          }
           *p = out;
         }
       }

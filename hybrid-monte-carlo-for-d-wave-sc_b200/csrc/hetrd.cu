@@ -61,6 +61,49 @@ __device__ __forceinline__ cplx block_sum(cplx v, cplx* red) {
   return t;
 }
 
+// L2 residency hints: the panel columns of V and W are re-read by every column step of the panel
+// (evict_last), the trailing matrix streamed by hemv is not (evict_first).
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ cplx ld_keep(const cplx* p, unsigned long long pol) {
+  cplx v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_keep(cplx* p, cplx v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
+// acc -= sum_{k < cnt} Vr[k ld] cv[k] + Wr[k ld] cw[k]; loads issued in batches of 8 + 8 so that a
+// thread has 16 independent requests in flight (the loop is latency-bound otherwise)
+__device__ __forceinline__ void panel_row_update(cplx& acc, const cplx* Vr, const cplx* Wr, size_t ld, const cplx* cv,
+                                                 const cplx* cw, int cnt, unsigned long long pol) {
+  for (int k = 0; k < cnt; k += 8) {
+    cplx v[8], w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool p = k + u < cnt;
+      v[u] = p ? ld_keep(Vr + (size_t)(k + u) * ld, pol) : make_double2(0.0, 0.0);
+      w[u] = p ? ld_keep(Wr + (size_t)(k + u) * ld, pol) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (k + u < cnt) {
+        cfms(acc, v[u], cv[k + u]);
+        cfms(acc, w[u], cw[k + u]);
+      }
+    }
+  }
+}
+
 struct ColArgs {
   cplx* A; cplx* V; cplx* W; cplx* ypart; cplx* P1; cplx* P2; cplx* tau;
   double* d; double* e;
@@ -96,6 +139,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
   cplx* A = g.A + mat;
   cplx* V = g.V + mat;
   cplx* W = g.W + mat;
+  const unsigned long long pol = policy_evict_last();
 
   if (g.finish_prev) {
     const int jp = j - 1, ip = jp - j0;
@@ -115,12 +159,9 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     for (int r = lo + tid; r < hi; r += CT) {
       cplx acc = make_double2(0.0, 0.0);
       for (int s = 0; s < nslots; ++s) acc = cadd(acc, g.ypart[((size_t)s * g.B + b) * n + r]);
-      for (int k = 0; k < ip; ++k) {
-        cfms(acc, V[(size_t)(j0 + k) * n + r], rowW[k]);
-        cfms(acc, W[(size_t)(j0 + k) * n + r], rowV[k]);
-      }
+      panel_row_update(acc, V + (size_t)j0 * n + r, W + (size_t)j0 * n + r, n, rowW, rowV, ip, pol);
       const cplx wv = cmul(tau, acc);
-      const cplx vv = V[(size_t)jp * n + r];
+      const cplx vv = ld_keep(V + (size_t)jp * n + r, pol);
       sw[r - lo] = wv;
       sv[r - lo] = vv;
       cfmac(dot, wv, vv);
@@ -135,7 +176,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     for (int r = lo + tid; r < hi; r += CT) {
       cplx wv = sw[r - lo];
       cfma(wv, alpha, sv[r - lo]);
-      W[(size_t)jp * n + r] = wv;
+      st_keep(W + (size_t)jp * n + r, wv, pol);
       if (r == j) xch[4] = wv;
     }
     if (!g.make_ref) {
@@ -163,10 +204,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     cplx nrm = make_double2(0.0, 0.0);
     for (int r = lo + tid; r < hi; r += CT) {
       cplx a = A[(size_t)j * n + r];
-      for (int k = 0; k < i; ++k) {
-        cfms(a, V[(size_t)(j0 + k) * n + r], rowW[k]);
-        cfms(a, W[(size_t)(j0 + k) * n + r], rowV[k]);
-      }
+      panel_row_update(a, V + (size_t)j0 * n + r, W + (size_t)j0 * n + r, n, rowW, rowV, i, pol);
       sw[r - lo] = a;
       if (r >= j + 2) nrm.x += a.x * a.x + a.y * a.y;
       if (r == j) xch[2] = a;
@@ -205,7 +243,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     for (int r = max(lo, j + 1) + tid; r < hi; r += CT) {
       const cplx v = (r == j + 1) ? make_double2(1.0, 0.0) : cmul(sw[r - lo], scale);
       sv[r - lo] = v;
-      V[(size_t)j * n + r] = v;
+      st_keep(V + (size_t)j * n + r, v, pol);
     }
     __syncthreads();
     // partial products over this CTA's rows: P1[k] = W[:, j0+k]^H v, P2[k] = V[:, j0+k]^H v (k < i)
@@ -215,7 +253,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
       const int k = q >> 1, which = q & 1;
       const cplx* src = (which ? V : W) + (size_t)(j0 + k) * n;
       cplx acc = make_double2(0.0, 0.0);
-      for (int r = r0 + lane; r < hi; r += 32) cfmac(acc, src[r], sv[r - lo]);
+      for (int r = r0 + lane; r < hi; r += 32) cfmac(acc, ld_keep(src + r, pol), sv[r - lo]);
       acc = warp_sum(acc);
       if (lane == 0) {
         if (which) g.P2[((size_t)b * CC + rank) * DW_NB + k] = acc;
@@ -235,10 +273,11 @@ constexpr int TS = 64;
 constexpr int TLD = TS + 1;   // padded: the column pass reads with stride TLD, conflict-free
 constexpr size_t HEMV_SMEM = sizeof(cplx) * (TS * TLD + 2 * TS + 8 * TS);
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred, unsigned long long pol) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(sa), "l"(gmem), "r"(sz),
+               "l"(pol));
 }
 
 __global__ void __launch_bounds__(256) hemv_lower_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
@@ -263,12 +302,13 @@ __global__ void __launch_bounds__(256) hemv_lower_kernel(const cplx* __restrict_
   const size_t mat = (size_t)b * n * n;
   const cplx* A = Aall + mat + (size_t)(q0 + C0) * n + q0 + R0;
   const cplx* v = Vall + mat + (size_t)j * n + q0;
+  const unsigned long long pol = policy_evict_first();
 #pragma unroll
   for (int it = 0; it < (TS * TS) / 256; ++it) {
     const int idx = tid + it * 256;
     const int r = idx & (TS - 1), c = idx >> 6;
     const bool p = (R0 + r < m) && (C0 + c < m);
-    cp_async16(As + c * TLD + r, p ? A + (size_t)c * n + r : A, p);
+    cp_async16(As + c * TLD + r, p ? A + (size_t)c * n + r : A, p, pol);
   }
   asm volatile("cp.async.commit_group;\n" ::);
   if (tid < TS) vr[tid] = (R0 + tid < m) ? v[R0 + tid] : make_double2(0.0, 0.0);
@@ -332,20 +372,33 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
     attr_set[h->device & 63] = true;
   }
   if (col_smem > 200 * 1024) { h->err = "dw_hetrd: matrix too large for the column-step kernel"; return DWHMC_E_BADARG; }
-  // The batch is split into groups that run on their own streams: the latency-bound column step of
-  // one group (one CTA per chain) overlaps the HBM-bound hemv of the other.
+  // The batch is split into groups.  Each group has a high-priority stream for the latency-bound
+  // column step (few CTAs) and a low-priority stream for the bulk kernels (hemv, her2k), chained by
+  // events, so the column step of one group is scheduled ahead of the queued hemv tiles of the
+  // others and overlaps them instead of waiting for their tail.
   const int G = (B >= 2 * h->ngroups && n >= 256 && h->profiling < 2) ? h->ngroups : 1;
-  cudaStream_t st[DW_NGROUP];
+  cudaStream_t hp[DW_NGROUP], lp[DW_NGROUP];
   int gb0[DW_NGROUP], gB[DW_NGROUP];
   for (int g = 0; g < G; ++g) {
     gb0[g] = (int)((long long)B * g / G);
     gB[g] = (int)((long long)B * (g + 1) / G) - gb0[g];
-    st[g] = (G == 1) ? h->stream : h->gstream[g];
+    hp[g] = (G == 1) ? h->stream : h->gstream_hi[g];
+    lp[g] = (G == 1) ? h->stream : h->gstream[g];
   }
   if (G > 1) {
     DW_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-    for (int g = 0; g < G; ++g) DW_CUDA(h, cudaStreamWaitEvent(st[g], h->ev_fork, 0));
+    for (int g = 0; g < G; ++g) {
+      DW_CUDA(h, cudaStreamWaitEvent(hp[g], h->ev_fork, 0));
+      DW_CUDA(h, cudaStreamWaitEvent(lp[g], h->ev_fork, 0));
+    }
   }
+  // bulk -> column step and column step -> bulk hand-over (no-ops when both are the same stream)
+  auto bulk_done = [&](int g) {
+    if (G > 1) { cudaEventRecord(h->ev_bulk[g], lp[g]); cudaStreamWaitEvent(hp[g], h->ev_bulk[g], 0); }
+  };
+  auto col_done = [&](int g) {
+    if (G > 1) { cudaEventRecord(h->ev_col[g], hp[g]); cudaStreamWaitEvent(lp[g], h->ev_col[g], 0); }
+  };
   ColArgs ca;
   ca.A = h->A; ca.V = h->V; ca.W = W; ca.ypart = h->ypart; ca.P1 = h->P1; ca.P2 = h->P2; ca.tau = h->tau;
   ca.d = h->d; ca.e = h->e; ca.n = n; ca.B = B; ca.mask = mask;
@@ -358,26 +411,29 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       const int nt = (m + TS - 1) / TS;
       for (int g = 0; g < G; ++g) {
         ca.j = j; ca.finish_prev = (i > 0); ca.make_ref = 1; ca.b0 = gb0[g];
-        colstep_kernel<<<gB[g] * CC, CT, col_smem, st[g]>>>(ca);
+        colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
         DW_LAUNCH_CHECK(h);
+        col_done(g);
         dim3 grid(nt * (nt + 1) / 2, gB[g]);
-        if (h->profiling >= 2) cudaEventRecord(h->ev_begin, st[g]);
-        hemv_lower_kernel<<<grid, 256, HEMV_SMEM, st[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        if (h->profiling >= 2) cudaEventRecord(h->ev_begin, lp[g]);
+        hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
         DW_LAUNCH_CHECK(h);
         if (h->profiling >= 2) {
-          cudaEventRecord(h->ev_end, st[g]);
+          cudaEventRecord(h->ev_end, lp[g]);
           cudaEventSynchronize(h->ev_end);
           float ms = 0.f;
           cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
           h->timers[7] += ms;
         }
+        bulk_done(g);
       }
     }
     const int j1 = j0 + pn;
     for (int g = 0; g < G; ++g) {
       ca.j = j1; ca.finish_prev = 1; ca.make_ref = 0; ca.b0 = gb0[g];
-      colstep_kernel<<<gB[g] * CC, CT, col_smem, st[g]>>>(ca);
+      colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
       DW_LAUNCH_CHECK(h);
+      col_done(g);
       // trailing update A[j1:, j1:] -= V W^H + W V^H, lower-triangle tiles only
       ZgemmArgs a;
       a.M = n - j1; a.N = n - j1; a.K = pn; a.nseg = 2;
@@ -387,13 +443,14 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       a.sA = (long long)n * n; a.sB = (long long)n * n; a.sC = (long long)n * n;
       a.C = h->A + (size_t)j1 * n + j1;
       a.alpha = -1.0; a.beta = 1.0; a.opA = 0; a.opB = 1; a.lower = 1; a.batch = gB[g]; a.mask = mask;
-      a.b0 = gb0[g]; a.stream = st[g];
+      a.b0 = gb0[g]; a.stream = lp[g];
       DW_TRY(dw_zgemm(h, a));
+      bulk_done(g);
     }
   }
   if (G > 1) {
     for (int g = 0; g < G; ++g) {
-      DW_CUDA(h, cudaEventRecord(h->ev_join[g], st[g]));
+      DW_CUDA(h, cudaEventRecord(h->ev_join[g], hp[g]));
       DW_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[g], 0));
     }
   }

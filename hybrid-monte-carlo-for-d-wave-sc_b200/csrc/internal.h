@@ -42,8 +42,9 @@ struct Handle {
   int profiling = 0;             // 1: stage timers; 2: also per-launch hemv timing (serialises the groups)
   double timers[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_end = nullptr;
-  cudaStream_t gstream[DW_NGROUP] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[DW_NGROUP] = {};
+  cudaStream_t gstream[DW_NGROUP] = {};      // bulk kernels of a chain group (low priority)
+  cudaStream_t gstream_hi[DW_NGROUP] = {};   // column steps of a chain group (high priority)
+  cudaEvent_t ev_fork = nullptr, ev_join[DW_NGROUP] = {}, ev_bulk[DW_NGROUP] = {}, ev_col[DW_NGROUP] = {};
   double last_ms = 0.0;          // device time of the last dwhmc_run_sweeps (events on `stream`)
   std::vector<void*> allocs;    // everything cudaMalloc'ed, for destroy
 
