@@ -3,6 +3,8 @@
 // Used for the dense contractions of the eigensolver: the rank-2k trailing update of the
 // tridiagonalisation (her2k as one two-segment GEMM, lower tiles only) and the block-reflector
 // products of the eigenvector back-transformation.  One complex 8x8x4 product = 4 DMMA.
+#include <cstdlib>
+
 #include "dwhmc.h"
 #include "gemm_dmma.cuh"
 #include "internal.h"
@@ -35,8 +37,10 @@ struct KArgs {
   Mask mask;
 };
 
+// two CTAs per SM whenever the tile's shared memory allows it (<= 128 registers per thread)
 template <int BM, int BN, int WM, int WN, int OPA, int OPB>
-__global__ void __launch_bounds__(NTHREADS) zgemm_dmma_kernel(KArgs g) {
+__global__ void __launch_bounds__(NTHREADS, (Tile<BM, BN, OPA, OPB>::SMEM <= 113 * 1024) ? 2 : 1)
+zgemm_dmma_kernel(KArgs g) {
   using T = Tile<BM, BN, OPA, OPB>;
   constexpr int WTM = BM / WM, WTN = BN / WN;   // warp tile
   constexpr int MI = WTM / 8, NI = WTN / 8;
@@ -163,15 +167,24 @@ __global__ void __launch_bounds__(NTHREADS) zgemm_dmma_kernel(KArgs g) {
         br[j] = v.x;
         bi[j] = (OPB == 0) ? v.y : -v.y;
       }
+      // four passes of MI*NI independent DMMAs: the two updates of one accumulator are 2*MI*NI
+      // instructions apart, so no DMMA waits on the latency of its predecessor
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NI; ++j) {
-          dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
-          dmma884(cr[i][j][0], cr[i][j][1], nai[i], bi[j]);
-          dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
-          dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
-        }
+        for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(cr[i][j][0], cr[i][j][1], nai[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
     }
   }
   cp_async_wait<0>();
@@ -223,13 +236,18 @@ int dw_zgemm(Handle* h, const ZgemmArgs& a) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return DWHMC_OK;
   if (a.K <= 0 && a.beta == 1.0) return DWHMC_OK;
   const bool small_m = a.M <= 32;
+  static int big = -1;                  // DWHMC_GEMM_BIG=1: 128x64 tiles for the tall updates (experiment)
+  if (big < 0) { const char* e = getenv("DWHMC_GEMM_BIG"); big = e ? atoi(e) : 0; }
+  const bool tall = big && a.M >= 256;
   if (a.opA == 0 && a.opB == 1) {
+    if (tall) return launch<128, 64, 4, 2, 0, 1>(h, a);
     return launch<64, 64, 2, 4, 0, 1>(h, a);
   } else if (a.opA == 1 && a.opB == 0) {
     if (small_m) return launch<32, 128, 1, 8, 1, 0>(h, a);
     return launch<64, 64, 2, 4, 1, 0>(h, a);
   } else if (a.opA == 0 && a.opB == 0) {
     if (small_m) return launch<32, 128, 1, 8, 0, 0>(h, a);
+    if (tall) return launch<128, 64, 4, 2, 0, 0>(h, a);
     return launch<64, 64, 2, 4, 0, 0>(h, a);
   }
   h->err = "dw_zgemm: unsupported op combination";

@@ -8,7 +8,9 @@
 
 #include "stedc_tree.h"
 
-#define DW_NB 32          // Householder panel width (tridiagonalisation and back-transform blocks)
+#ifndef DW_NB
+#define DW_NB 32          // Householder panel width of the tridiagonalisation
+#endif
 #define DW_CC 4           // CTAs per cluster in the column-step kernel
 #define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
 #define DW_LEAF 36        // largest D&C leaf

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, "libdwhmc.so")
+LIB_PATH = os.environ.get("DWHMC_LIB", os.path.join(_PKG_DIR, "libdwhmc.so"))
 
 OK, E_BADARG, E_CUDA, E_NOCONV, E_NODEVICE, E_STATE = range(6)
 NOBS = 9
