@@ -82,10 +82,13 @@ __device__ __forceinline__ void st_keep(cplx* p, cplx v, unsigned long long pol)
   asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
 
-// acc -= sum_{k < cnt} Vr[k ld] cv[k] + Wr[k ld] cw[k]; loads issued in batches of 8 + 8 so that a
-// thread has 16 independent requests in flight (the loop is latency-bound otherwise)
-__device__ __forceinline__ void panel_row_update(cplx& acc, const cplx* Vr, const cplx* Wr, size_t ld, const cplx* cv,
-                                                 const cplx* cw, int cnt, unsigned long long pol) {
+// One pass over the panel rows V[r, :], W[r, :] (k < cnt) feeding two accumulators:
+//   accF -= V[r,k] f1[k] + W[r,k] f2[k]     (finish w_{j-1})
+//   accR -= V[r,k] c1[k] + W[r,k] c2[k]     (update column j)
+// Loads are issued in batches of 8 + 8 so a thread has 16 independent requests in flight.
+__device__ __forceinline__ void panel_row_update2(cplx& accF, cplx& accR, const cplx* Vr, const cplx* Wr, size_t ld,
+                                                  const cplx* f1, const cplx* f2, const cplx* c1, const cplx* c2,
+                                                  int cnt, bool doR, unsigned long long pol) {
   for (int k = 0; k < cnt; k += 8) {
     cplx v[8], w[8];
 #pragma unroll
@@ -97,8 +100,12 @@ __device__ __forceinline__ void panel_row_update(cplx& acc, const cplx* Vr, cons
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       if (k + u < cnt) {
-        cfms(acc, v[u], cv[k + u]);
-        cfms(acc, w[u], cw[k + u]);
+        cfms(accF, v[u], f1[k + u]);
+        cfms(accF, w[u], f2[k + u]);
+        if (doR) {
+          cfms(accR, v[u], c1[k + u]);
+          cfms(accR, w[u], c2[k + u]);
+        }
       }
     }
   }
@@ -129,9 +136,12 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
   const int chunk_max = (n + CC - 1) / CC;
   cplx* sv = reinterpret_cast<cplx*>(smem_raw);   // [chunk_max] reflector rows of this CTA
   cplx* sw = sv + chunk_max;                      // [chunk_max] w, then the updated column a
-  cplx* rowW = sw + chunk_max;                    // [NB]
-  cplx* rowV = rowW + DW_NB;                      // [NB]
-  cplx* red = rowV + DW_NB;                       // [32]
+  cplx* sa = sw + chunk_max;                      // [chunk_max] column j minus the panel terms k < i - 1
+  cplx* rowW = sa + chunk_max;                    // [NB] W_panel^H v_{j-1}
+  cplx* rowV = rowW + DW_NB;                      // [NB] V_panel^H v_{j-1}
+  cplx* cW = rowV + DW_NB;                        // [NB] conj(W[j, panel])
+  cplx* cV = cW + DW_NB;                          // [NB] conj(V[j, panel])
+  cplx* red = cV + DW_NB;                         // [32]
   __shared__ cplx xch[8];                         // DSMEM exchange: 0 dot, 1 norm, 2 a[j], 3 a[j+1], 4 w[j]
   __shared__ cplx s_scale;
   const int lo = j + rank * chunk, hi = min(n, lo + chunk);
@@ -140,6 +150,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
   cplx* V = g.V + mat;
   cplx* W = g.W + mat;
   const unsigned long long pol = policy_evict_last();
+  const int i = j - j0;
 
   if (g.finish_prev) {
     const int jp = j - 1, ip = jp - j0;
@@ -151,6 +162,11 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
       }
       rowW[tid] = p1;
       rowV[tid] = p2;
+      if (g.make_ref) {
+        const cplx a = W[(size_t)(j0 + tid) * n + j], c = V[(size_t)(j0 + tid) * n + j];
+        cW[tid] = make_double2(a.x, -a.y);
+        cV[tid] = make_double2(c.x, -c.y);
+      }
     }
     const cplx tau = g.tau[(size_t)b * n + jp];
     const int nslots = (n - jp - 1 + 63) / 64;     // tiles per dimension of the hemv of column jp
@@ -158,12 +174,23 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     cplx dot = make_double2(0.0, 0.0);
     for (int r = lo + tid; r < hi; r += CT) {
       cplx acc = make_double2(0.0, 0.0);
-      for (int s = 0; s < nslots; ++s) acc = cadd(acc, g.ypart[((size_t)s * g.B + b) * n + r]);
-      panel_row_update(acc, V + (size_t)j0 * n + r, W + (size_t)j0 * n + r, n, rowW, rowV, ip, pol);
+      for (int s0 = 0; s0 < nslots; s0 += 8) {       // up to 8 independent loads in flight, fixed summation order
+        cplx y[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          y[u] = (s0 + u < nslots) ? g.ypart[((size_t)(s0 + u) * g.B + b) * n + r] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = cadd(acc, y[u]);
+      }
+      cplx accR = g.make_ref ? A[(size_t)j * n + r] : make_double2(0.0, 0.0);
+      // one pass over the panel rows serves both w_{j-1} and the update of column j (terms k < i - 1)
+      panel_row_update2(acc, accR, V + (size_t)j0 * n + r, W + (size_t)j0 * n + r, n, rowW, rowV, cW, cV, ip,
+                        g.make_ref != 0, pol);
       const cplx wv = cmul(tau, acc);
       const cplx vv = ld_keep(V + (size_t)jp * n + r, pol);
       sw[r - lo] = wv;
       sv[r - lo] = vv;
+      sa[r - lo] = accR;
       cfmac(dot, wv, vv);
     }
     dot = block_sum(dot, red);
@@ -176,6 +203,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     for (int r = lo + tid; r < hi; r += CT) {
       cplx wv = sw[r - lo];
       cfma(wv, alpha, sv[r - lo]);
+      sw[r - lo] = wv;
       st_keep(W + (size_t)jp * n + r, wv, pol);
       if (r == j) xch[4] = wv;
     }
@@ -186,25 +214,24 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
   }
 
   {
-    const int i = j - j0;
-    cluster.sync();         // W[:, j-1] complete; xch[4] of rank 0 valid
-    if (tid < i) {
-      cplx a, c;
-      if (g.finish_prev && tid == i - 1) {
-        a = cluster.map_shared_rank(xch, 0)[4];          // W[j, j-1], owned by rank 0
-        c = make_double2(1.0, 0.0);                      // V[j, j-1] is the unit entry
-      } else {
-        a = W[(size_t)(j0 + tid) * n + j];
-        c = V[(size_t)(j0 + tid) * n + j];
-      }
-      rowW[tid] = make_double2(a.x, -a.y);
-      rowV[tid] = make_double2(c.x, -c.y);
+    cluster.sync();         // xch[4] of rank 0 (= W[j, j-1]) valid
+    cplx wj = make_double2(0.0, 0.0);
+    if (g.finish_prev) {
+      const cplx t = cluster.map_shared_rank(xch, 0)[4];
+      wj = make_double2(t.x, -t.y);
     }
-    __syncthreads();
     cplx nrm = make_double2(0.0, 0.0);
     for (int r = lo + tid; r < hi; r += CT) {
-      cplx a = A[(size_t)j * n + r];
-      panel_row_update(a, V + (size_t)j0 * n + r, W + (size_t)j0 * n + r, n, rowW, rowV, i, pol);
+      cplx a;
+      if (g.finish_prev) {
+        // last panel term k = i - 1: V[r, j-1] conj(W[j, j-1]) + W[r, j-1] conj(V[j, j-1]), V[j, j-1] = 1
+        a = sa[r - lo];
+        cfms(a, sv[r - lo], wj);
+        const cplx wr = sw[r - lo];
+        a.x -= wr.x; a.y -= wr.y;
+      } else {
+        a = A[(size_t)j * n + r];       // first column of a panel: the trailing matrix is up to date
+      }
       sw[r - lo] = a;
       if (r >= j + 2) nrm.x += a.x * a.x + a.y * a.y;
       if (r == j) xch[2] = a;
@@ -247,17 +274,44 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     }
     __syncthreads();
     // partial products over this CTA's rows: P1[k] = W[:, j0+k]^H v, P2[k] = V[:, j0+k]^H v (k < i)
+    // Warp w accumulates the products q = w, w + 8, ... (up to 8 of the 2 i <= 64) at once, so each
+    // pass over the rows keeps 8-16 independent loads in flight instead of one product at a time.
     const int nw = CT / 32;
     const int r0 = max(lo, j + 1);
-    for (int q = warp; q < 2 * i; q += nw) {
-      const int k = q >> 1, which = q & 1;
-      const cplx* src = (which ? V : W) + (size_t)(j0 + k) * n;
-      cplx acc = make_double2(0.0, 0.0);
-      for (int r = r0 + lane; r < hi; r += 32) cfmac(acc, ld_keep(src + r, pol), sv[r - lo]);
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        if (which) g.P2[((size_t)b * CC + rank) * DW_NB + k] = acc;
-        else g.P1[((size_t)b * CC + rank) * DW_NB + k] = acc;
+    const int ndots = 2 * i;
+    if (warp < ndots) {
+      const cplx* src[8];
+      cplx acc[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int q = min(warp + nw * t, ndots - 1);
+        src[t] = ((q & 1) ? V : W) + (size_t)(j0 + (q >> 1)) * n;
+        acc[t] = make_double2(0.0, 0.0);
+      }
+      for (int r = r0 + lane; r < hi; r += 64) {
+        const bool two = r + 32 < hi;
+        const cplx v0 = sv[r - lo];
+        const cplx v1 = two ? sv[r + 32 - lo] : make_double2(0.0, 0.0);
+        cplx x0[8], x1[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          x0[t] = ld_keep(src[t] + r, pol);
+          x1[t] = two ? ld_keep(src[t] + r + 32, pol) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          cfmac(acc[t], x0[t], v0);
+          cfmac(acc[t], x1[t], v1);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int q = warp + nw * t;
+        const cplx sum = warp_sum(acc[t]);
+        if (lane == 0 && q < ndots) {
+          if (q & 1) g.P2[((size_t)b * CC + rank) * DW_NB + (q >> 1)] = sum;
+          else g.P1[((size_t)b * CC + rank) * DW_NB + (q >> 1)] = sum;
+        }
       }
     }
     cluster.sync();         // exchange slots stay alive until every CTA has read them
@@ -364,7 +418,7 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
     DW_LAUNCH_CHECK(h);
     return DWHMC_OK;
   }
-  const size_t col_smem = sizeof(cplx) * (2 * (size_t)((n + CC - 1) / CC) + 2 * DW_NB + 32);
+  const size_t col_smem = sizeof(cplx) * (3 * (size_t)((n + CC - 1) / CC) + 4 * DW_NB + 32);
   static bool attr_set[64] = {false};
   if (!attr_set[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(colstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

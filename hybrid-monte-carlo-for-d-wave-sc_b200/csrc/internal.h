@@ -11,7 +11,10 @@
 #ifndef DW_NB
 #define DW_NB 32          // Householder panel width of the tridiagonalisation
 #endif
-#define DW_CC 4           // CTAs per cluster in the column-step kernel
+#ifndef DW_CC
+#define DW_CC 4
+#endif
+//      DW_CC:           // CTAs per cluster in the column-step kernel
 #define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
 #define DW_LEAF 36        // largest D&C leaf
 #define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
