@@ -223,14 +223,33 @@ __global__ void __launch_bounds__(256) dc_copy_kernel(LevelArgs g) {
   }
 }
 
-__global__ void __launch_bounds__(128) dc_secular_kernel(LevelArgs g) {
+// warp-parallel reduction policy for secular_root (same interface as dwcore::SerialPar): lanes
+// stride over the poles; the butterfly sum leaves bit-identical totals in every lane, so the
+// iteration's control flow stays uniform across the warp
+struct WarpPar {
+  int lane;
+  __device__ __forceinline__ int begin() const { return lane; }
+  __device__ __forceinline__ int stride() const { return 32; }
+  __device__ __forceinline__ void sum4(double& a, double& b, double& c, double& d) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+  }
+};
+
+// one warp per root of the secular equation; 8 roots per CTA share the staged poles
+__global__ void __launch_bounds__(256) dc_secular_kernel(LevelArgs g) {
   const int b = blockIdx.z;
   if (!g.mask.on(b)) return;
   const int off = g.off[blockIdx.y];
   const int n = g.n;
   const size_t vo = (size_t)b * n + off;
   const int k = g.kcnt[vo];
-  if ((int)(blockIdx.x * blockDim.x) >= k) return;
+  if ((int)(blockIdx.x * 8) >= k) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sdl = reinterpret_cast<double*>(smem_raw);
   double* sw = sdl + k;
@@ -239,16 +258,19 @@ __global__ void __launch_bounds__(128) dc_secular_kernel(LevelArgs g) {
     sw[i] = g.wv[vo + i];
   }
   __syncthreads();
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
   if (j >= k) return;
-  SerialPar par;
+  WarpPar par{lane};
   int org;
   double tau;
   const int it = secular_root(k, j, sdl, sw, g.rho[vo], par, &org, &tau);
-  if (it < 0) atomicAdd(&g.status[1], 1);
-  g.sorg[vo + j] = org;
-  g.stau[vo + j] = tau;
-  g.dnew[vo + j] = sdl[org] + tau;
+  if (lane == 0) {
+    if (it < 0) atomicAdd(&g.status[1], 1);
+    g.sorg[vo + j] = org;
+    g.stau[vo + j] = tau;
+    g.dnew[vo + j] = sdl[org] + tau;
+  }
 }
 
 // Gu/Eisenstat: zhat_i^2 = prod_j (lambda_j - d_i) / prod_{j != i} (d_j - d_i)
@@ -495,9 +517,10 @@ int dw_stedc(Handle* h, Mask mask) {
       DW_LAUNCH_CHECK(h);
     }
     {
-      dim3 grid((mm + 127) / 128, lv.nmerge, B);
-      dc_secular_kernel<<<grid, 128, (size_t)mm * 16, h->stream>>>(g);
+      dim3 sgrid((mm + 7) / 8, lv.nmerge, B);
+      dc_secular_kernel<<<sgrid, 256, (size_t)mm * 16, h->stream>>>(g);
       DW_LAUNCH_CHECK(h);
+      dim3 grid((mm + 127) / 128, lv.nmerge, B);
       dc_zhat_kernel<<<grid, 128, (size_t)mm * 24, h->stream>>>(g);
       DW_LAUNCH_CHECK(h);
     }
