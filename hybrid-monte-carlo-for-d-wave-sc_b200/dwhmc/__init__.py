@@ -6,3 +6,4 @@ from .batch import ChainBatch, OBS_NAMES, calc_optimal_dt, neighbour_tables  # n
 from .reference_api import (ComputeCache, ModelParameters, ObservablesResult, SimulationState,  # noqa: F401
                             compute_forces, compute_total_energy, diagonalize_H_BdG, hmc_sweep, init_static_H,
                             initialize_cache, initialize_state, measure_observables, refresh_momentum, update_H_BdG)
+from .simulation import batch_scan_T, run_simulation, run_simulation_batch  # noqa: E402,F401

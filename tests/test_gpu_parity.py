@@ -328,3 +328,41 @@ def test_device_rng_statistics(dw):
     x = np.concatenate([pi.real.ravel(), pi.imag.ravel()])
     assert abs(x.mean()) < 0.1 and abs(x.var() - 2.0) < 0.2      # Re, Im ~ N(0, m = 2)
     cb.close()
+
+
+def test_batched_run_driver_matches_oracle_run(dw, tmp_path):
+    """run_simulation (src/Simulation.jl:34-236) for two chains at once, host-RNG mode: the adaptive
+    thermalisation decisions, accept flags, dH and the nine observables of every measured sweep equal
+    a sequential oracle run that consumes the same generator; files have the reference's layout."""
+    from dwhmc import simulation as sim
+    L, n_therm, n_meas, Nt0, Ntm = 4, 10, 6, 4, 5
+    betas, seeds = [5.0, 40.0], [11, 12]
+    ps = [dw.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.1, b, PHYS["J"], PHYS["mass"]) for b in betas]
+    dirs = [str(tmp_path / sim.scan_dir_T(1.0 / b)) for b in betas]
+    out = sim.run_simulation_batch(ps, dirs, n_therm=n_therm, n_measure=n_meas, Nt_therm_init=Nt0, Nt_measure=Ntm,
+                                   seeds=seeds, rng_mode="host")
+    for c, (beta, seed) in enumerate(zip(betas, seeds)):
+        p = orc.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.1, beta, PHYS["J"], PHYS["mass"])
+        rng, st, ca = orc.make_chain(p, seed)
+        Nt, recent = Nt0, 0
+        dt = orc.calc_optimal_dt(p.beta, p.J, p.mass, Nt)
+        for i in range(1, n_therm + 1):
+            acc, _ = orc.hmc_sweep(ca, p, st, Nt=Nt, dt=dt, rng=rng)
+            recent += acc
+            if i % 5 == 0:
+                Nt = sim.adapt_Nt(recent / 5, Nt); recent = 0
+                dt = orc.calc_optimal_dt(p.beta, p.J, p.mass, Nt)
+        assert out["Nt_therm_final"][c] == Nt
+        dtm = orc.calc_optimal_dt(p.beta, p.J, p.mass, Ntm)
+        rows = open(os.path.join(dirs[c], "observables.csv")).read().splitlines()
+        assert rows[0] == sim.OBS_HEADER and len(rows) == n_meas + 1
+        for i in range(1, n_meas + 1):
+            acc, dH, Ho, _ = orc.hmc_sweep(ca, p, st, Nt=Ntm, dt=dtm, rng=rng, return_energies=True)
+            obs = orc.measure_observables(ca, p, st)
+            row = out["table"][i - 1, c]
+            assert row[0] == i and bool(row[1]) == acc
+            assert abs(row[2] - dH) <= 1e-9 * max(abs(Ho), 1.0)
+            assert np.allclose(row[3:], obs, rtol=1e-7, atol=1e-9)
+            assert rows[i] == sim.obs_csv_line(i, acc, row[2], row[3:]).rstrip("\n")
+        assert open(os.path.join(dirs[c], "transport.csv")).read().strip() == sim.TRANS_HEADER
+        assert "Measurement Done." in open(os.path.join(dirs[c], "simulation.log")).read()

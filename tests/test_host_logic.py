@@ -97,3 +97,20 @@ def test_gather_world2_gloo(built, tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0 and b"ok" in out, out.decode()
+
+
+def test_run_driver_formats_and_adaptive_Nt(built):
+    """Host logic of the batched run driver: CSV row format (src/Simulation.jl:161-165), directory
+    names (scripts/batch_scan_T.jl:62), adaptive-Nt rule (src/Simulation.jl:116-120)."""
+    from dwhmc import simulation as sim
+    line = sim.obs_csv_line(7, True, -1.23456789e-3, [0.1 * k for k in range(9)])
+    assert line == "7,1,-1.23457e-03,0.000000,0.100000,0.200000,0.300000,0.400000,0.500000,0.600000,0.700000,0.800000\n"
+    assert sim.OBS_HEADER.count(",") == 11 and line.count(",") == 11
+    assert [sim.adapt_Nt(r, n) for r, n in ((0.4, 10), (0.6, 10), (0.96, 10), (1.0, 4), (1.0, 5))] == [12, 10, 9, 4, 4]
+    for x, s in ((0.0001, "0.0001"), (0.00001, "1.0e-5"), (1000.0, "1000.0"), (0.000201, "0.000201"), (12.5, "12.5"),
+                 (1.0e6, "1.0e6"), (123456.0, "123456.0"), (2.03e-5, "2.03e-5"), (0.5, "0.5"), (1e21, "1.0e21")):
+        assert sim.julia_float_str(x) == s, (x, sim.julia_float_str(x))
+    Ts = 10.0 ** np.linspace(-4, 3, 24)
+    assert sim.scan_dir_T(Ts[0]) == "T_0.0001" and sim.scan_dir_T(Ts[-1]) == "T_1000.0"
+    assert sim.scan_dir_T(Ts[1]) == "T_0.000202"
+    assert sim.scan_dir_beta(0.01) == "beta_0.01" and sim.scan_dir_beta(100000.0) == "beta_100000.0"
