@@ -113,6 +113,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     const int v = atoi(eg);
     if (v >= 1 && v <= DW_NGROUP) h->ngroups = v;
   }
+  if (const char* ep = getenv("DWHMC_PH")) h->ph_mode = atoi(ep) ? 1 : 0;
   auto fail = [&](int rc) { g_create_err = h->err; dwhmc_destroy(hs); return rc; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DWHMC_E_CUDA); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
@@ -163,6 +164,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     h->rots = r;
   }
   AL(h->kcnt, nB); AL(h->nrot, nB); AL(h->rho, nB); AL(h->status, 4);
+  AL(h->halfflag, (size_t)B);
   // D&C tree (shared by all chains)
   h->tree = build_dc_tree(n, DW_LEAF);
   h->nleaves = (int)h->tree.leaves.size();
@@ -298,7 +300,7 @@ int dwhmc_diagonalize(dwhmc_handle hh) {
     StageTimer t(h, 0);
     DW_TRY(dw_assemble(h, h->Hs_w, h->Hs_par, h->Hs_delta, h->A, no_mask()));
   }
-  DW_TRY(dw_eigensolve(h, h->E_cur, h->U_cur, no_mask()));
+  DW_TRY(dw_eigensolve(h, h->E_cur, h->U_cur, no_mask(), true));
   DW_CUDA(h, cudaStreamSynchronize(h->stream));
   return check_status(h);
 }
@@ -372,7 +374,7 @@ static int trajectory_enqueue(Handle* h, int max_nt, bool device_momentum) {
       StageTimer t(h, 0);
       DW_TRY(dw_assemble(h, h->Hs_w, h->Hs_par, h->delta, h->A, mask));
     }
-    DW_TRY(dw_eigensolve(h, h->E_prop, h->U_prop, mask));
+    DW_TRY(dw_eigensolve(h, h->E_prop, h->U_prop, mask, true));
     StageTimer t(h, 4);
     DW_TRY(dw_forces(h, h->E_prop, h->U_prop, 1, s));
   }
@@ -529,7 +531,7 @@ int dwhmc_debug_stedc(dwhmc_handle hh, const double* d, const double* e, double*
   DW_TRY(h2d(h, h->d, d, sizeof(double) * (size_t)n * B));
   DW_TRY(h2d(h, h->e, tmp.data(), sizeof(double) * (size_t)n * B));
   DW_TRY(dw_stedc(h, no_mask()));
-  DW_TRY(dw_stedc_output(h, h->E_prop, h->U_prop, no_mask()));
+  DW_TRY(dw_stedc_output(h, h->E_prop, h->U_prop, no_mask(), false));
   DW_TRY(d2h(h, w, h->E_prop, sizeof(double) * (size_t)n * B));
   std::vector<double> zc((size_t)2 * n * n * B);
   DW_TRY(d2h(h, zc.data(), h->U_prop, sizeof(cplx) * (size_t)n * n * B));
@@ -543,7 +545,7 @@ int dwhmc_debug_heev(dwhmc_handle hh, const double* A, double* E, double* U) {
   if (h->pending) { h->err = "dwhmc_debug_heev: a trajectory proposal is pending"; return DWHMC_E_STATE; }
   const int n = h->n, B = h->B;
   DW_TRY(h2d(h, h->A, A, sizeof(cplx) * (size_t)n * n * B));
-  DW_TRY(dw_eigensolve(h, h->E_prop, h->U_prop, no_mask()));
+  DW_TRY(dw_eigensolve(h, h->E_prop, h->U_prop, no_mask(), false));
   DW_TRY(d2h(h, E, h->E_prop, sizeof(double) * (size_t)n * B));
   DW_TRY(d2h(h, U, h->U_prop, sizeof(cplx) * (size_t)n * n * B));
   return check_status(h);

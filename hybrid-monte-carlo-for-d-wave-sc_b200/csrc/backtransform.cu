@@ -49,13 +49,39 @@ __global__ void __launch_bounds__(DW_NBT) bt_larft_kernel(const cplx* __restrict
   for (int c = 0; c < DW_NBT; ++c) out[c * DW_NBT + r] = Tr[c];
 }
 
+// Partner columns of the particle-hole symmetric spectrum: (u, v) with energy E  ->  (-conj v, conj u)
+// with energy -E (tau_y H^* tau_y = -H for H = [[h, D], [D^*, -h]], h real, D symmetric).
+__global__ void __launch_bounds__(256) ph_mirror_kernel(double* __restrict__ Eall, cplx* __restrict__ Uall,
+                                                        const int* __restrict__ halfflag, int N, Mask mask) {
+  const int b = blockIdx.y;
+  if (!mask.on(b) || halfflag[b] == 0) return;
+  const int n = 2 * N, k = blockIdx.x, src = n - 1 - k;
+  cplx* U = Uall + (size_t)b * n * n;
+  const cplx* s = U + (size_t)src * n;
+  cplx* d = U + (size_t)k * n;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const cplx u = s[i], v = s[i + N];
+    d[i] = make_double2(-v.x, v.y);
+    d[i + N] = make_double2(u.x, -u.y);
+  }
+  if (threadIdx.x == 0) Eall[(size_t)b * n + k] = -Eall[(size_t)b * n + src];
+}
+
 }  // namespace
 
-int dw_backtransform(Handle* h, cplx* U, Mask mask) {
+int dw_ph_mirror(Handle* h, double* E, cplx* U, Mask mask) {
+  dim3 grid(h->N, h->B);
+  ph_mirror_kernel<<<grid, 256, 0, h->stream>>>(E, U, h->halfflag, h->N, mask);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
+int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   const int n = h->n, B = h->B, nbt = h->nbt;
   const long long sT = (long long)nbt * DW_NBT * DW_NBT;
   ZgemmArgs a;
   a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
+  const bool half = ph && h->ph_mode;
   // Gram matrices of all blocks, then their T factors
   for (int k = 0; k < nbt; ++k) {
     const int j0 = k * DW_NBT;
@@ -88,6 +114,7 @@ int dw_backtransform(Handle* h, cplx* U, Mask mask) {
     const cplx* Vk = h->V + (size_t)j0 * n + (j0 + 1);   // rows j0+1.., columns j0..j0+pn-1
     cplx* Uk = U + (j0 + 1);                             // rows j0+1.. of every column
     // W1 (pn x n) = V_k^H U_k
+    if (half) { a.skip_flag = h->halfflag; a.skip_cols = h->N; }
     a.M = pn; a.N = n; a.K = mk;
     a.A[0] = Vk; a.lda = n; a.sA = (long long)n * n; a.opA = 1;
     a.Bm[0] = Uk; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
@@ -112,7 +139,7 @@ int dw_backtransform(Handle* h, cplx* U, Mask mask) {
   return DWHMC_OK;
 }
 
-int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask) {
+int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
   // U_out doubles as the W panel scratch of the tridiagonalisation (it is only written with
   // eigenvectors after that stage has finished)
   cudaEvent_t& e0 = h->ev0;
@@ -131,10 +158,11 @@ int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask) {
   toc(1);
   tic();
   DW_TRY(dw_stedc(h, mask));
-  DW_TRY(dw_stedc_output(h, E_out, U_out, mask));
+  DW_TRY(dw_stedc_output(h, E_out, U_out, mask, ph));
   toc(2);
   tic();
-  DW_TRY(dw_backtransform(h, U_out, mask));
+  DW_TRY(dw_backtransform(h, U_out, mask, ph));
+  if (ph && h->ph_mode) DW_TRY(dw_ph_mirror(h, E_out, U_out, mask));
   toc(3);
   h->eigensolves++;
   return DWHMC_OK;

@@ -35,6 +35,8 @@ struct KArgs {
   int lower;
   int b0;
   Mask mask;
+  const int* skip_flag;
+  int skip_cols;
 };
 
 // two CTAs per SM whenever the tile's shared memory allows it (<= 128 registers per thread)
@@ -52,6 +54,7 @@ zgemm_dmma_kernel(KArgs g) {
   if (!g.mask.on(b)) return;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (g.lower && n0 > m0 + BM - 1) return;
+  if (g.skip_flag != nullptr && n0 + BN <= g.skip_cols && g.skip_flag[b] != 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp % WM) * WTM, wn0 = (warp / WM) * WTN;
 
@@ -224,8 +227,14 @@ int launch(Handle* h, const ZgemmArgs& a) {
   g.lda = a.lda; g.ldb = a.ldb; g.ldc = a.ldc;
   g.sA = a.sA; g.sB = a.sB; g.sC = a.sC;
   g.C = a.C; g.alpha = a.alpha; g.beta = a.beta; g.lower = a.lower; g.mask = a.mask; g.b0 = a.b0;
+  g.skip_flag = a.skip_flag; g.skip_cols = a.skip_cols;
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
-  kern<<<grid, NTHREADS, T::SMEM, a.stream ? a.stream : h->stream>>>(g);
+  static int pad = -1;                  // DWHMC_GEMM_PAD=KB: extra dynamic smem (experiment: limit CTAs/SM)
+  if (pad < 0) {
+    const char* e = getenv("DWHMC_GEMM_PAD"); pad = e ? atoi(e) * 1024 : 0;
+    if (pad) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM + pad);
+  }
+  kern<<<grid, NTHREADS, T::SMEM + pad, a.stream ? a.stream : h->stream>>>(g);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }

@@ -119,6 +119,10 @@ struct Handle {
   double* rho = nullptr;        // [n*B]
   int* status = nullptr;        // [4] device: [0] leaf failures, [1] secular non-convergence
   int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
+  // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
+  // upper half of the spectrum are back-transformed, the rest are their conjugate partners
+  int ph_mode = 1;              // env DWHMC_PH=0 switches the shortcut off
+  int* halfflag = nullptr;      // device [B]: 1 = this chain's last eigensolve used the shortcut
   long long launches = 0;
   long long eigensolves = 0;
 };
@@ -157,13 +161,16 @@ int dw_assemble(Handle* h, const double* w, const double* par3, const cplx* delt
 int dw_assemble_upper(Handle* h, const double* w, const double* par3, const cplx* delta, cplx* out);
 // hetrd.cu: h->A -> h->d, h->e, h->V, h->tau, h->Tf ; Wscratch is an n*n*B complex scratch
 int dw_hetrd(Handle* h, cplx* Wscratch, Mask mask);
-// stedc.cu: h->d, h->e -> eigenvalues E_out (ascending) and real eigenvectors written as complex into U_out
+// stedc.cu: h->d, h->e -> eigenvalues E_out (ascending) and real eigenvectors written as complex into U_out.
+// ph: decide per chain (h->halfflag) whether the particle-hole shortcut applies; flagged chains only get
+// the columns of the upper half of the spectrum.
 int dw_stedc(Handle* h, Mask mask);
-int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask);
-// backtransform.cu: U <- Q U
-int dw_backtransform(Handle* h, cplx* U, Mask mask);
-// A (assembled, destroyed) -> E, U
-int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask);
+int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph);
+// backtransform.cu: U <- Q U (flagged chains: upper-half columns only, then the partner columns)
+int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
+int dw_ph_mirror(Handle* h, double* E, cplx* U, Mask mask);
+// A (assembled, destroyed) -> E, U.  ph: the matrix is a BdG matrix assembled by dw_assemble.
+int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph);
 
 // generic batched complex GEMM on FP64 tensor cores (gemm_dmma.cu)
 // C = beta*C + alpha * sum_seg opA(A_seg) * opB(B_seg);  opX: 0 = N, 1 = C (conjugate transpose)
@@ -180,6 +187,8 @@ struct ZgemmArgs {
   int batch;
   Mask mask;
   int b0 = 0;                  // first chain of the launch (chain groups)
+  const int* skip_flag = nullptr;  // device [B] or null: chains with flag != 0 skip the column tiles that
+  int skip_cols = 0;               //   lie entirely below column skip_cols
   cudaStream_t stream = nullptr;   // nullptr = the handle's stream
 };
 int dw_zgemm(Handle* h, const ZgemmArgs& a);

@@ -458,15 +458,37 @@ __global__ void __launch_bounds__(256) dc_finish_kernel(LevelArgs g) {
   }
 }
 
-// eigenvalues ascending + eigenvectors as complex columns of U
-__global__ void __launch_bounds__(256) dc_output_kernel(const double* __restrict__ D, const int* __restrict__ perm,
-                                                        const double* __restrict__ Z, double* __restrict__ E_out,
-                                                        cplx* __restrict__ U_out, int n, Mask mask) {
+// eigenvalues ascending; decide whether the particle-hole shortcut is safe for this chain: the
+// partner construction needs the second-smallest level of the upper half to be resolved from zero
+// (a pair (E, -E) alone is always fine, <psi, C psi> = 0 exactly; two pairs closer to zero than the
+// solver's resolution are not)
+__global__ void __launch_bounds__(256) dc_evals_kernel(const double* __restrict__ D, const int* __restrict__ perm,
+                                                       double* __restrict__ E_out, int* __restrict__ halfflag, int n,
+                                                       int ph, Mask mask) {
+  const int b = blockIdx.x;
+  if (!mask.on(b)) return;
+  double* E = E_out + (size_t)b * n;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) E[r] = D[(size_t)b * n + perm[(size_t)b * n + r]];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int flag = 0;
+    if (ph && n >= 8) {
+      const double emax = fmax(fabs(E[0]), fabs(E[n - 1]));
+      flag = (E[n / 2 + 1] > 1e-4 * emax) ? 1 : 0;
+    }
+    halfflag[b] = flag;
+  }
+}
+
+// eigenvectors as complex columns of U (flagged chains: columns >= c_lo only)
+__global__ void __launch_bounds__(256) dc_output_kernel(const int* __restrict__ perm, const double* __restrict__ Z,
+                                                        cplx* __restrict__ U_out, const int* __restrict__ halfflag,
+                                                        int c_lo, int n, Mask mask) {
   const int b = blockIdx.y;
   if (!mask.on(b)) return;
   const int r = blockIdx.x;
+  if (r < c_lo && halfflag[b] != 0) return;
   const int c = perm[(size_t)b * n + r];
-  if (threadIdx.x == 0) E_out[(size_t)b * n + r] = D[(size_t)b * n + c];
   const double* src = Z + (size_t)b * n * n + (size_t)c * n;
   cplx* dst = U_out + (size_t)b * n * n + (size_t)r * n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = make_double2(src[i], 0.0);
@@ -548,9 +570,14 @@ int dw_stedc(Handle* h, Mask mask) {
   return DWHMC_OK;
 }
 
-int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask) {
+int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
+  dc_evals_kernel<<<h->B, 256, 0, h->stream>>>(h->d, h->perm, E_out, h->halfflag, h->n, (ph && h->ph_mode) ? 1 : 0, mask);
+  DW_LAUNCH_CHECK(h);
   dim3 grid(h->n, h->B);
-  dc_output_kernel<<<grid, 256, 0, h->stream>>>(h->d, h->perm, h->Zfinal, E_out, U_out, h->n, mask);
+  // the GEMM tiles of the back-transformation are at most 128 columns wide: keep every column a
+  // straddling tile may touch
+  const int c_lo = (h->N / 128) * 128;
+  dc_output_kernel<<<grid, 256, 0, h->stream>>>(h->perm, h->Zfinal, U_out, h->halfflag, c_lo, h->n, mask);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }

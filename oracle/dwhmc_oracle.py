@@ -359,6 +359,105 @@ def measure_observables(cache: ComputeCache, p: ModelParameters, state: Simulati
 
 
 # --------------------------------------------------------------------------
+# src/Observables.jl:237-526  (transport and spectra)
+# --------------------------------------------------------------------------
+def julia_range(start: float, step: float, stop: float) -> np.ndarray:
+    """collect(start:step:stop) for Float64 (length = floor((stop-start)/step + 1e-10) + 1; the
+    reference's grids eta:d_omega:omega_max and -omega_max:d_omega:omega_max)."""
+    n = int(math.floor((stop - start) / step + 1e-10)) + 1
+    return start + step * np.arange(max(n, 0), dtype=np.float64)
+
+
+def build_current_operator(p: ModelParameters) -> np.ndarray:
+    """src/Observables.jl:237-283 as a dense 2N x 2N matrix: blockdiag(Jx, Jx),
+    Jx[i, i+x] += i t, Jx[i+x, i] += -i t, same with t' for i+x+y and i+x-y (duplicates add, as sparse())."""
+    N = p.N
+    Jp = np.zeros((N, N), dtype=np.complex128)
+    for i in range(N):
+        for j, val in ((p.nn_table[i, 0], 1j * p.t), (p.nnn_table[i, 0], 1j * p.tp), (p.nnn_table[i, 3], 1j * p.tp)):
+            Jp[i, j] += val
+            Jp[j, i] += np.conj(val)
+    J = np.zeros((2 * N, 2 * N), dtype=np.complex128)
+    J[:N, :N] = Jp
+    J[N:, N:] = Jp
+    return J
+
+
+def lorentzian(x, eta):
+    return (1.0 / math.pi) * (eta / (x * x + eta * eta))
+
+
+@dataclass
+class SpectrumResult:
+    """src/Observables.jl:293-311."""
+    superfluid_stiffness: float
+    dc_conductivity: float
+    omega_grid: np.ndarray
+    optical_conductivity: np.ndarray
+    dos_omega_grid: np.ndarray
+    dos: np.ndarray
+    dos_AN: np.ndarray
+    A_k_w0: np.ndarray
+
+
+def measure_transport_and_spectra(cache: ComputeCache, p: ModelParameters) -> SpectrumResult:
+    """src/Observables.jl:314-526.  Requires cache.fermi_factors current (the reference reads
+    cache.fermi_factors as left by the last compute_forces!/measure_observables call)."""
+    N, dim, beta = p.N, 2 * p.N, p.beta
+    U, E, f = cache.U, cache.E_n, cache.fermi_factors
+    Jx = build_current_operator(p)
+    J_mn = U.conj().T @ (Jx @ U)                                     # :334-335
+    J2 = np.abs(J_mn) ** 2
+    # B. stiffness (:346-387)
+    jx, jxpy, jxmy = p.nn_table[:, 0], p.nnn_table[:, 0], p.nnn_table[:, 3]
+    Up, Un = U[:N], U[N:]
+    val_dia = 0.0
+    for n in range(dim):
+        if E[n] > 0:
+            u, v = Up[:, n], Un[:, n]
+            w_n = 0.0
+            for nb, hop in ((jx, p.t), (jxpy, p.tp), (jxmy, p.tp)):
+                w_n += hop * 2.0 * float(np.sum((v * np.conj(v[nb]) - np.conj(u) * u[nb]).real))
+            val_dia += w_n * math.tanh(0.5 * beta * E[n]) / N
+    dE = E[None, :] - E[:, None]                                     # [n, m] = E[m] - E[n]
+    df = f[:, None] - f[None, :]                                     # f[n] - f[m]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(np.abs(dE) < 1e-8, (beta * f * (1.0 - f))[:, None] * np.ones_like(dE), df / dE)
+    Lambda_xx = float(np.sum(ratio * J2)) / N
+    stiffness = val_dia - Lambda_xx
+    # C. conductivities (:398-425)
+    eta = p.eta
+    omega_grid = julia_range(p.eta, p.d_omega, p.omega_max)
+    dc = float(np.sum((beta * f * (1.0 - f))[:, None] * J2 * lorentzian(dE, eta))) * (math.pi / N)
+    sigma = np.zeros(len(omega_grid))
+    wgt = np.where(np.abs(df) < 1e-12, 0.0, df) * J2
+    sel = wgt != 0.0
+    wsel, dsel = wgt[sel], dE[sel]
+    for iw, w in enumerate(omega_grid):
+        sigma[iw] = float(np.sum((wsel / w) * lorentzian(w - dsel, eta)))
+    sigma *= math.pi / N
+    # D. DOS, antinodal DOS, A(k, 0) (:431-519)
+    dos_grid = julia_range(-p.omega_max, p.d_omega, p.omega_max)
+    w_n = np.sum(np.abs(Up) ** 2, axis=0)
+    xs = np.arange(N) % p.Lx + 1                                     # 1-based x, y as in mod1 / cld
+    ys = np.arange(N) // p.Lx + 1
+    sx = np.where(xs % 2 == 0, 1.0, -1.0)
+    sy = np.where(ys % 2 == 0, 1.0, -1.0)
+    w_AN = 0.5 * (np.abs(sx @ Up) ** 2 + np.abs(sy @ Up) ** 2) / N
+    L = lorentzian(dos_grid[:, None] - E[None, :], eta)
+    dos = (L @ w_n) / N
+    dos_AN = L @ w_AN
+    w0 = lorentzian(0.0 - E, eta)
+    ak = np.zeros((p.Lx, p.Ly))
+    for n in range(dim):
+        if w0[n] > 1e-6:
+            ur = Up[:, n].reshape(p.Ly, p.Lx).T                      # u_r[x, y], i = (y-1) Lx + x
+            ak += np.abs(np.fft.fft2(ur)) ** 2 * w0[n]               # FFTW forward = exp(-2 pi i ...)
+    ak /= N
+    return SpectrumResult(stiffness, dc, omega_grid, sigma, dos_grid, dos, dos_AN, ak)
+
+
+# --------------------------------------------------------------------------
 # src/Simulation.jl:11-14
 # --------------------------------------------------------------------------
 def calc_optimal_dt(beta: float, J: float, mass: float, Nt: int) -> float:

@@ -235,6 +235,65 @@ def test_degenerate_and_extreme_spectra(dw):
     cb.close()
 
 
+def test_particle_hole_shortcut_and_fallback(dw, monkeypatch):
+    """The eigensolver back-transforms only the upper half of the spectrum and builds the partner
+    columns (u, v) -> (-conj v, conj u) (tau_y H^* tau_y = -H).  (i) It must agree with the full
+    back-transformation (DWHMC_PH=0); (ii) when more than one pair of levels sits at zero (here:
+    mu = t' = 0, zero field: exact zero modes on the whole line kx + ky = pi) the chain falls back
+    to the full path, and U is still a unitary eigenbasis with the oracle's correlators."""
+    L, B = 8, 3
+    N, n = L * L, 2 * L * L
+    betas = np.array([2.0, 20.0, 200.0])
+    rng = np.random.default_rng(77)
+    w = np.zeros((B, N)); w[:, rng.permutation(N)[:3]] = 1.0
+    delta = (rng.random((B, 2, N)) - 0.5 + 1j * (rng.random((B, 2, N)) - 0.5)) * 0.3
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DWHMC_PH", mode)
+        cb = dw.ChainBatch(B, L, L)
+        cb.set_params(1.0, -0.35, -1.08, betas, 0.8, 1.0)
+        cb.set_disorder(w); cb.set_field(delta)
+        cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG(); cb.compute_forces()
+        res[mode] = (cb.get_eigenvalues(), cb.get_eigenvectors(), cb.get_forces(), cb.measure_observables(),
+                     cb.get_H())
+        cb.close()
+    monkeypatch.delenv("DWHMC_PH")
+    E1, U1, F1, O1, H1 = res["1"]
+    E0, U0, F0, O0, _ = res["0"]
+    assert np.max(np.abs(E1 - E0)) <= 1e-13 * np.max(np.abs(E0))
+    assert rel(F1, F0) <= 1e-12
+    assert np.allclose(O1, O0, rtol=1e-11, atol=1e-13)
+    for b in range(B):
+        Hu = H1[b].T
+        Hf = np.triu(Hu) + np.triu(Hu, 1).conj().T
+        Ub = U1[b].T
+        assert np.max(np.abs(Ub.conj().T @ Ub - np.eye(n))) <= 1e-12
+        assert np.max(np.abs(Hf @ Ub - Ub * E1[b])) <= 1e-12 * np.max(np.abs(E1[b]))
+        # partner structure of the shortcut: column k is C applied to column n-1-k
+        assert np.max(np.abs(Ub[:N, :N] + Ub[N:, :N - 1:-1].conj())) <= 1e-15
+    # fallback: massively degenerate zero modes
+    ps, sts, cs = [], [], []
+    for b, beta in enumerate(betas):
+        p = orc.ModelParameters(L, L, 1.0, 0.0, 0.0, 1.0, 0.0, float(beta), 0.8, 1.0)
+        _, st, c = orc.make_chain(p, 900 + b)
+        st.Delta[...] = 0.0
+        orc.update_H_BdG(c, p, st); orc.diagonalize_H_BdG(c, p); orc.compute_forces(c, p, st)
+        ps.append(p); sts.append(st); cs.append(c)
+    cb = dw.ChainBatch(B, L, L)
+    cb.set_params(1.0, 0.0, 0.0, betas, 0.8, 1.0)
+    cb.set_disorder(np.zeros((B, N))); cb.set_field(np.zeros((B, 2, N), complex))
+    cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG(); cb.compute_forces()
+    E, U, F = cb.get_eigenvalues(), cb.get_eigenvectors(), cb.get_forces()
+    for b in range(B):
+        Ub = U[b].T
+        Hf = orc.full_hermitian(cs[b])
+        assert np.sum(np.abs(E[b]) < 1e-12) >= 4          # the zero modes are there
+        assert np.max(np.abs(Ub.conj().T @ Ub - np.eye(n))) <= 1e-12
+        assert np.max(np.abs(Hf @ Ub - Ub * E[b])) <= 1e-12 * np.max(np.abs(E[b]))
+        assert np.max(np.abs(F[b].T - cs[b].forces)) <= 1e-10 * max(np.max(np.abs(cs[b].forces)), 1.0)
+    cb.close()
+
+
 def test_debug_stages(dw):
     import scipy.linalg as sl
     B, L = 2, 6
