@@ -114,6 +114,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     if (v >= 1 && v <= DW_NGROUP) h->ngroups = v;
   }
   if (const char* ep = getenv("DWHMC_PH")) h->ph_mode = atoi(ep) ? 1 : 0;
+  if (const char* ev = getenv("DWHMC_HEMV")) h->hemv_variant = atoi(ev);
   auto fail = [&](int rc) { g_create_err = h->err; dwhmc_destroy(hs); return rc; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DWHMC_E_CUDA); }
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
@@ -165,6 +166,16 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   }
   AL(h->kcnt, nB); AL(h->nrot, nB); AL(h->rho, nB); AL(h->status, 4);
   AL(h->halfflag, (size_t)B);
+  if ((rc = dw_band_setup(h, nn, nnn)) != DWHMC_OK) return fail(rc);
+  if (h->band_b > 0) {
+    const size_t nblk = h->band_blk_s0.size();
+    AL(h->band_pos, (size_t)n); AL(h->band_prog, nB); AL(h->band_tau, nB * h->band_KT);
+    AL(h->band_T, nblk * 64 * 64 * B);
+    AL(h->band_blk_s0_dev, nblk); AL(h->band_blk_k_dev, nblk);
+    if ((rc = h2d(h, h->band_pos, h->band_pos_host.data(), sizeof(int) * n)) != DWHMC_OK) return fail(rc);
+    if ((rc = h2d(h, h->band_blk_s0_dev, h->band_blk_s0.data(), sizeof(int) * nblk)) != DWHMC_OK) return fail(rc);
+    if ((rc = h2d(h, h->band_blk_k_dev, h->band_blk_k.data(), sizeof(int) * nblk)) != DWHMC_OK) return fail(rc);
+  }
   // D&C tree (shared by all chains)
   h->tree = build_dc_tree(n, DW_LEAF);
   h->nleaves = (int)h->tree.leaves.size();
@@ -298,7 +309,7 @@ int dwhmc_diagonalize(dwhmc_handle hh) {
   H_ENTER(hh);
   {
     StageTimer t(h, 0);
-    DW_TRY(dw_assemble(h, h->Hs_w, h->Hs_par, h->Hs_delta, h->A, no_mask()));
+    DW_TRY(dw_assemble_for_solve(h, h->Hs_w, h->Hs_par, h->Hs_delta, no_mask()));
   }
   DW_TRY(dw_eigensolve(h, h->E_cur, h->U_cur, no_mask(), true));
   DW_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -372,7 +383,7 @@ static int trajectory_enqueue(Handle* h, int max_nt, bool device_momentum) {
     Mask mask; mask.nt = h->nt_dev; mask.step = s;
     {
       StageTimer t(h, 0);
-      DW_TRY(dw_assemble(h, h->Hs_w, h->Hs_par, h->delta, h->A, mask));
+      DW_TRY(dw_assemble_for_solve(h, h->Hs_w, h->Hs_par, h->delta, mask));
     }
     DW_TRY(dw_eigensolve(h, h->E_prop, h->U_prop, mask, true));
     StageTimer t(h, 4);
@@ -511,8 +522,9 @@ int dwhmc_set_profiling(dwhmc_handle hh, int on) {
 int dwhmc_debug_tridiagonalize(dwhmc_handle hh, double* d, double* e) {
   H_ENTER(hh);
   if (!d || !e) BADARG("dwhmc_debug_tridiagonalize: NULL");
-  DW_TRY(dw_assemble(h, h->Hs_w, h->Hs_par, h->Hs_delta, h->A, no_mask()));
-  DW_TRY(dw_hetrd(h, h->U_prop, no_mask()));
+  DW_TRY(dw_assemble_for_solve(h, h->Hs_w, h->Hs_par, h->Hs_delta, no_mask()));
+  if (h->band_b > 0) DW_TRY(dw_band_chase(h, no_mask()));
+  else DW_TRY(dw_hetrd(h, h->U_prop, no_mask()));
   std::vector<double> tmp((size_t)h->n * h->B);
   DW_TRY(d2h(h, d, h->d, sizeof(double) * (size_t)h->n * h->B));
   DW_TRY(d2h(h, tmp.data(), h->e, sizeof(double) * (size_t)h->n * h->B));

@@ -139,6 +139,11 @@ int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   return DWHMC_OK;
 }
 
+int dw_assemble_for_solve(Handle* h, const double* w, const double* par3, const cplx* delta, Mask mask) {
+  if (h->band_b > 0) return dw_band_assemble(h, w, par3, delta, mask);
+  return dw_assemble(h, w, par3, delta, h->A, mask);
+}
+
 int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
   // U_out doubles as the W panel scratch of the tridiagonalisation (it is only written with
   // eigenvectors after that stage has finished)
@@ -153,15 +158,19 @@ int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
     cudaEventElapsedTime(&ms, e0, e1);
     h->timers[slot] += ms;
   };
+  const bool band = ph && h->band_b > 0;
   tic();
-  DW_TRY(dw_hetrd(h, U_out, mask));
+  if (band) DW_TRY(dw_band_chase(h, mask));
+  else DW_TRY(dw_hetrd(h, U_out, mask));
   toc(1);
   tic();
   DW_TRY(dw_stedc(h, mask));
-  DW_TRY(dw_stedc_output(h, E_out, U_out, mask, ph));
+  // band route: the tridiagonal eigenvectors go to h->A (the band is dead by now), in band row order
+  DW_TRY(dw_stedc_output(h, E_out, band ? h->A : U_out, mask, ph));
   toc(2);
   tic();
-  DW_TRY(dw_backtransform(h, U_out, mask, ph));
+  if (band) DW_TRY(dw_band_backtransform(h, U_out, mask, ph));
+  else DW_TRY(dw_backtransform(h, U_out, mask, ph));
   if (ph && h->ph_mode) DW_TRY(dw_ph_mirror(h, E_out, U_out, mask));
   toc(3);
   h->eigensolves++;

@@ -1,0 +1,713 @@
+// band.cu -- band route of diagonalize_H_BdG! (/root/reference src/Hamiltonian.jl:96-114).
+//
+// The BdG matrix of a periodic Lx x Ly lattice is sparse (13 entries per row).  With the sites of
+// each ring folded (0, L-1, 1, L-2, ...) and particle / hole components interleaved it is a band
+// matrix of half-bandwidth b = 4 min(Lx, Ly) + 4 (100 of n = 1152 at L = 24), so the dense -> band
+// stage of a two-stage eigensolver is free.  This file holds the rest:
+//   assemble_band   H straight into lower band storage  AB[d + j LD] = H[j + d, j], LD = 2b
+//   chase           band -> real tridiagonal by Householder bulge chasing (Lang's algorithm):
+//                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; a persistent CTA per sweep
+//                   in flight, sweeps of a chain pipelined three steps apart through release/acquire
+//                   progress counters; the block pushed out by a step stays in shared memory for
+//                   the next one (3 b^2 elements of global traffic per step)
+//   tfactor + back-transformation   U = Q2 Z: reflectors of g consecutive sweeps at the same step
+//                   form one staircase block reflector, applied as three DMMA GEMMs (gemm_dmma.cu)
+//   unpermute       rows back to the reference's site order
+// The numerics (LAPACK-style zlarfg / zhetd2 updates, application order of the blocks) are the
+// ones prototyped against LAPACK in tests/algo_proto_band.py.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "dwhmc.h"
+#include "internal.h"
+
+namespace {
+
+constexpr int CT = 512;             // threads per CTA of the chase kernel
+constexpr int CW = CT / 32;         // warps
+constexpr int RQ = 5;               // row chunks of 32 per lane: b <= 160
+
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {       // acc += a b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfms(cplx& acc, cplx a, cplx b) {       // acc -= a b
+  acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(cplx& acc, cplx a, cplx b) {      // acc += conj(a) b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+__device__ __forceinline__ cplx block_sum(cplx v, cplx* red) {          // result in every thread, fixed order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  cplx t = make_double2(0.0, 0.0);
+  for (int i = 0; i < CW; ++i) t = cadd(t, red[i]);
+  return t;
+}
+// the band is shared between the CTAs of a chain: all accesses go to L2 (no stale L1 lines)
+__device__ __forceinline__ cplx ldg2(const cplx* p) {
+  cplx v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg2(cplx* p, cplx v) {
+  asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- assembly into band storage ------------------------------------------------------------------
+// pos[r]: band index of row r of the reference's matrix (r < N particle of site r, r >= N hole)
+__global__ void band_scatter_kernel(cplx* __restrict__ ABall, const double* __restrict__ w, const double* __restrict__ par3,
+                                    const cplx* __restrict__ delta, const int* __restrict__ nn, const int* __restrict__ nnn,
+                                    const int* __restrict__ pos, int N, int B, int LD, Mask mask) {
+  const int b = blockIdx.y;
+  if (!mask.on(b)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int n = 2 * N;
+  cplx* AB = ABall + (size_t)b * n * LD;
+  const double t = par3[b], tp = par3[B + b], mu = par3[2 * B + b];
+  const double term = w[(size_t)b * N + i] - mu;
+  auto put = [&](int r, int c, double re, double im) {     // entry (r, c) of the Hermitian matrix
+    const int pr = pos[r], pc = pos[c];
+    if (pr >= pc) AB[(size_t)pc * LD + (pr - pc)] = make_double2(re, im);
+    else AB[(size_t)pr * LD + (pc - pr)] = make_double2(re, -im);
+  };
+  put(i, i, term, 0.0);
+  put(i + N, i + N, -term, 0.0);
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int j = nn[d * N + i];
+    if (j != i) { put(i, j, -t, 0.0); put(i + N, j + N, t, 0.0); }
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    const int j = nnn[d * N + i];
+    if (j != i) { put(i, j, -tp, 0.0); put(i + N, j + N, tp, 0.0); }
+  }
+  const cplx* dl = delta + (size_t)b * 2 * N;
+#pragma unroll
+  for (int dir = 0; dir < 2; ++dir) {
+    const int j = nn[dir * N + i];
+    const cplx v = dl[dir * N + i];
+    put(i, j + N, 0.5 * v.x, 0.5 * v.y);
+    put(j, i + N, 0.5 * v.x, 0.5 * v.y);
+  }
+}
+
+// ---- bulge chasing ---------------------------------------------------------------------------------
+struct ChaseArgs {
+  cplx* AB; cplx* V; cplx* tau2; int* prog;
+  int n, b, LD, KT, P, c0;       // c0: first chain of this launch
+  Mask mask;
+  long long* clk;                // optional [8] phase clock accumulators of CTA 0 (profiling experiments)
+};
+
+// LAPACK zlarfg on x (shared, length ln >= 1): v = x scaled, v[0] = 1 (left in vs); returns tau, beta.
+// Every thread gets the same (tau, beta).
+__device__ __forceinline__ void larfg_block(const cplx* xs, cplx* vs, int ln, cplx* red, cplx& tau, double& beta) {
+  const int tid = threadIdx.x;
+  cplx nrm = make_double2(0.0, 0.0);
+  for (int i = 1 + tid; i < ln; i += CT) { const cplx a = xs[i]; nrm.x += a.x * a.x + a.y * a.y; }
+  nrm = block_sum(nrm, red);
+  const cplx alpha = xs[0];
+  cplx scale;
+  if (nrm.x == 0.0 && alpha.y == 0.0) {
+    beta = alpha.x;
+    tau = make_double2(0.0, 0.0);
+    scale = make_double2(0.0, 0.0);
+  } else {
+    beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm.x), alpha.x);
+    tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+    const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+    scale = make_double2(dr / den, -di / den);
+  }
+  for (int i = tid; i < ln; i += CT) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
+  __syncthreads();
+}
+
+constexpr int EU = 20;              // elements of the b x b block per thread (b <= 101 at 512 threads)
+constexpr int DU = 10;              // elements of the folded lower triangle per thread
+
+// smem words of the chase kernel for half-bandwidth b (host and device must agree)
+__host__ __device__ inline size_t chase_smem_elems(int b) {
+  const int ldb = b | 1;
+  return (size_t)ldb * b + 6 * (size_t)b + 4 * (size_t)(32 * RQ) + 32;
+}
+
+// Folded enumeration of the lower triangle of an ln x ln block: columns c and ln-1-c together have
+// ln+1 entries.  slot -> (i, j); returns false for padding slots.
+__device__ __forceinline__ bool tri_slot(int slot, int ln, int& i, int& j) {
+  const int h = ln + 1;
+  const int c = slot / h, r = slot - c * h;
+  const int half = (ln + 1) >> 1;
+  if (c >= half) return false;
+  if (r < ln - c) { j = c; i = c + r; return true; }
+  if (2 * c + 1 == ln) return false;                 // middle column of an odd block has no partner
+  j = ln - 1 - c;
+  i = j + (r - (ln - c));
+  return true;
+}
+
+__global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
+  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
+  if (!g.mask.on(chain)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = g.n, b = g.b, LD = g.LD;
+  const int ldb = b | 1;                             // odd leading dimension: rows and columns both conflict-free
+  cplx* Bc = reinterpret_cast<cplx*>(smem_raw);      // [b][ldb] carried block / diagonal block, column-major
+  cplx* vs = Bc + (size_t)ldb * b;                   // current reflector
+  cplx* vp = vs + b;                                 // previous reflector (deferred right-application)
+  cplx* us = vp + b;                                 // Bc_raw vp
+  cplx* xs = us + b;                                 // column to annihilate / w
+  cplx* tu = xs + b;                                 // taup * us
+  cplx* wc = tu + b;                                 // conj(tau) z
+  cplx* part = wc + b;                               // [4][32 RQ] partial sums of the matrix-vector products
+  cplx* red = part + 4 * (32 * RQ);                  // [32]
+  const int tid = threadIdx.x;
+  cplx* AB = g.AB + (size_t)chain * n * LD;
+  cplx* V = g.V + (size_t)chain * n * n;
+  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
+  int* prog = g.prog + (size_t)chain * n;
+  const cplx zero = make_double2(0.0, 0.0);
+  // matrix-vector products from shared memory: thread = (row or column, part of the other index range)
+  const int rpad = (b + 31) & ~31;
+  const int nparts = min(4, CT / rpad);
+  const int mv_row = tid % rpad, mv_part = tid / rpad;
+  const int PS = 32 * RQ;
+
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
+#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+  for (int s = p; s < n - 1; s += g.P) {
+    int k = 0, r0 = s + 1;
+    cplx taup = zero;                                // tau of the previous step (carried block pending)
+    while (true) {
+      const int ln = min(b, n - r0);
+      if (prof) tlast = clock64();
+      if (k > 0 && ln <= 1) {
+        // nothing to annihilate: flush the carried block (ln rows x b columns) with its pending update
+        for (int idx = tid; idx < ln * b; idx += CT) {
+          const int i = idx % ln, j = idx / ln;
+          cplx a = Bc[(size_t)j * ldb + i];
+          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
+          stg2(AB + (size_t)(r0 - b + j) * LD + (b + i - j), a);
+        }
+        for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
+        break;
+      }
+      // wait until sweep s-1 is three steps ahead (or finished)
+      if (s > 0) {
+        if (tid == 0) {
+          const int need = k + 3;
+          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
+        }
+        __syncthreads();
+      }
+      PH(0);
+      // ---- prefetch the diagonal block (lower triangle, folded enumeration) into registers; it is
+      //      consumed after the carried block has been flushed out of shared memory
+      cplx dreg[DU];
+#pragma unroll
+      for (int u = 0; u < DU; ++u) {
+        int i, j;
+        dreg[u] = tri_slot(tid + u * CT, ln, i, j) ? ldg2(AB + (size_t)(r0 + j) * LD + (i - j)) : zero;
+      }
+      // ---- A. the column to annihilate
+      if (k == 0) {
+        for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
+      } else {
+        for (int i = tid; i < ln; i += CT) {
+          const cplx t = cmul(taup, us[i]);
+          tu[i] = t;
+          xs[i] = csub(Bc[i], t);                       // vp[0] = 1
+        }
+      }
+      __syncthreads();
+      // ---- B. reflector
+      cplx tau; double beta;
+      larfg_block(xs, vs, ln, red, tau, beta);
+      PH(1);
+      for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
+      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
+      if (k == 0) {
+        for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
+      } else {
+        // ---- C. carried block: pending right-application of (vp, taup) and left-application of H^H
+        //   new[i,j] = Bc[i,j] - tu[i] conj(vp[j]) - v[i] conj(tau) z[j],
+        //   z[j] = sum_i conj(v[i]) Bc[i,j] - conj(vp[j]) (v^H tu)
+        cplx c = zero;
+        for (int i = tid; i < ln; i += CT) cfmac(c, vs[i], tu[i]);
+        // column sums: thread = (column, part of the rows)
+        if (mv_part < nparts) {
+          cplx acc = zero;
+          if (mv_row < b) {
+            const int i0 = (int)((long long)ln * mv_part / nparts), i1 = (int)((long long)ln * (mv_part + 1) / nparts);
+            const cplx* col = Bc + (size_t)mv_row * ldb;
+            for (int i = i0; i < i1; ++i) cfmac(acc, vs[i], col[i]);
+          }
+          part[mv_part * PS + mv_row] = acc;
+        }
+        c = block_sum(c, red);                         // (its barriers also publish part[])
+        const cplx ctau = cconj(tau);
+        for (int j = tid; j < b; j += CT) {
+          cplx z = part[j];
+          for (int q = 1; q < nparts; ++q) z = cadd(z, part[q * PS + j]);
+          cfms(z, c, cconj(vp[j]));
+          wc[j] = cmul(ctau, z);
+        }
+        __syncthreads();
+        const int cb = r0 - b;                        // first column of the carried block
+        {
+          int i = tid % ln, j = tid / ln;
+          const int di = CT % ln, dj = CT / ln;
+          while (j < b) {
+            cplx o;
+            if (j == 0) {
+              o = (i == 0) ? make_double2(beta, 0.0) : zero;
+            } else {
+              o = Bc[(size_t)j * ldb + i];
+              cfms(o, tu[i], cconj(vp[j]));
+              cfms(o, vs[i], wc[j]);
+            }
+            stg2(AB + (size_t)(cb + j) * LD + (b - j) + i, o);
+            i += di; j += dj;
+            if (i >= ln) { i -= ln; ++j; }
+          }
+        }
+        __syncthreads();                              // Bc is reused below
+      }
+      PH(2);
+      // ---- D. diagonal block (rows / columns r0 .. r0+ln-1, lower triangle): A <- H^H A H
+      {
+#pragma unroll
+        for (int u = 0; u < DU; ++u) {
+          int i, j;
+          if (tri_slot(tid + u * CT, ln, i, j)) Bc[(size_t)j * ldb + i] = dreg[u];
+        }
+      }
+      // ---- prefetch the next block (rows r1 .. r1+l2-1, columns r0 .. r0+ln-1) into registers
+      const int r1 = r0 + ln;
+      const int l2 = (r1 < n) ? min(b, n - r1) : 0;
+      cplx ereg[EU];
+      {
+        const int tot = l2 * ln;
+        int i = (l2 > 0) ? tid % l2 : 0, j = (l2 > 0) ? tid / l2 : 0;
+        const int di = (l2 > 0) ? CT % l2 : 0, dj = (l2 > 0) ? CT / l2 : 0;
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          const bool ok = tid + u * CT < tot;
+          ereg[u] = ok ? ldg2(AB + (size_t)(r0 + j) * LD + (ln - j) + i) : zero;
+          i += di; j += dj;
+          if (l2 > 0 && i >= l2) { i -= l2; ++j; }
+        }
+      }
+      __syncthreads();
+      PH(3);
+      {
+        // x = tau D v with D Hermitian, lower triangle stored
+        if (mv_part < nparts) {
+          cplx acc = zero;
+          if (mv_row < ln) {
+            const int i = mv_row;
+            const int j0 = (int)((long long)ln * mv_part / nparts), j1 = (int)((long long)ln * (mv_part + 1) / nparts);
+            for (int j = j0; j < j1; ++j) {
+              const bool low = i >= j;
+              cplx a = Bc[low ? (size_t)j * ldb + i : (size_t)i * ldb + j];
+              if (!low) a.y = -a.y;
+              if (i == j) a.y = 0.0;
+              cfma(acc, a, vs[j]);
+            }
+          }
+          part[mv_part * PS + mv_row] = acc;
+        }
+        __syncthreads();
+        cplx dot = zero;
+        for (int i = tid; i < ln; i += CT) {
+          cplx wv = part[i];
+          for (int q = 1; q < nparts; ++q) wv = cadd(wv, part[q * PS + i]);
+          wv = cmul(tau, wv);                           // x = tau A v
+          xs[i] = wv;
+          cfmac(dot, wv, vs[i]);                        // x^H v
+        }
+        dot = block_sum(dot, red);
+        cplx alpha = cmul(tau, dot);
+        alpha.x *= -0.5; alpha.y *= -0.5;
+        for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < DU; ++u) {
+          int i, j;
+          if (tri_slot(tid + u * CT, ln, i, j)) {
+            cplx a = Bc[(size_t)j * ldb + i];
+            cfms(a, vs[i], cconj(xs[j]));
+            cfms(a, xs[i], cconj(vs[j]));
+            if (i == j) a.y = 0.0;
+            stg2(AB + (size_t)(r0 + j) * LD + (i - j), a);
+          }
+        }
+      }
+      // ---- E. next block: into shared memory, u = Bn v (the update itself is deferred to the next step)
+      if (l2 == 0) break;
+      __syncthreads();                                // the products above read Bc
+      PH(4);
+      {
+        const int tot = l2 * ln;
+        int i = tid % l2, j = tid / l2;
+        const int di = CT % l2, dj = CT / l2;
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+          if (tid + u * CT < tot) Bc[(size_t)j * ldb + i] = ereg[u];
+          i += di; j += dj;
+          if (i >= l2) { i -= l2; ++j; }
+        }
+        __syncthreads();
+        PH(5);
+        if (mv_part < nparts) {
+          cplx acc = zero;
+          if (mv_row < l2) {
+            const int j0 = (int)((long long)ln * mv_part / nparts), j1 = (int)((long long)ln * (mv_part + 1) / nparts);
+            for (int j = j0; j < j1; ++j) cfma(acc, Bc[(size_t)j * ldb + mv_row], vs[j]);
+          }
+          part[mv_part * PS + mv_row] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < l2; i += CT) {
+          cplx u = part[i];
+          for (int q = 1; q < nparts; ++q) u = cadd(u, part[q * PS + i]);
+          us[i] = u;
+        }
+        for (int i = tid; i < ln; i += CT) vp[i] = vs[i];
+        taup = tau;
+      }
+      // ---- F. publish
+      __syncthreads();
+      PH(6);
+      if (tid == 0) { __threadfence(); st_release(prog + s, k + 1); }
+      PH(7);
+      r0 = r1;
+      ++k;
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); st_release(prog + s, 1 << 30); }
+  }
+  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
+#undef PH
+}
+
+__global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restrict__ d, double* __restrict__ e, int n,
+                               int LD, Mask mask) {
+  const int b = blockIdx.y;
+  if (!mask.on(b)) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const cplx* col = ABall + ((size_t)b * n + j) * LD;
+  d[(size_t)b * n + j] = col[0].x;
+  e[(size_t)b * n + j] = (j + 1 < n) ? col[1].x : 0.0;
+}
+
+// ---- block reflectors of the back-transformation ---------------------------------------------------
+// block (s0, k): columns s0 .. s0+g-1 of V, rows rlo = s0+1+kb .. ; column c is non-zero on rows
+// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block.
+constexpr int TG = 64;               // max reflectors per block
+__global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restrict__ Vall, const cplx* __restrict__ tau2,
+                                                           cplx* __restrict__ Tall, const int* __restrict__ blk_s0,
+                                                           const int* __restrict__ blk_k, int n, int b, int g, int KT,
+                                                           int nblk, Mask mask) {
+  const int blk = blockIdx.x, ch = blockIdx.y;
+  if (!mask.on(ch)) return;
+  __shared__ cplx Vs[32 * TG];           // row chunk [32][g]
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* G = reinterpret_cast<cplx*>(smem_raw);          // [g][g] column-major
+  cplx* T = G + g * g;                                   // [g][g+1] row-major rows
+  const int s0 = blk_s0[blk], k = blk_k[blk];
+  const int gg = min(g, n - 1 - s0);                     // sweeps s0 .. s0+gg-1 exist
+  const int rlo = s0 + 1 + k * b;
+  const int rows = min(n - rlo, b + gg - 1);
+  const cplx* V = Vall + (size_t)ch * n * n;
+  const int tid = threadIdx.x;
+  const cplx zero = make_double2(0.0, 0.0);
+  // Gram matrix, lower part computed (c1 >= c2), accumulated over row chunks
+  constexpr int PAIRS = (TG * TG + 255) / 256;
+  cplx acc[PAIRS];
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) acc[q] = zero;
+  for (int rc = 0; rc < rows; rc += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < 32 * gg; idx += 256) {
+      const int r = idx & 31, c = idx >> 5;
+      const int rr = rc + r;
+      const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
+      Vs[c * 32 + r] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+      const int pidx = tid + 256 * q;
+      const int c1 = pidx % g, c2 = pidx / g;
+      if (c2 < gg && c1 < gg) {
+        cplx a = acc[q];
+        for (int r = 0; r < 32; ++r) cfmac(a, Vs[c1 * 32 + r], Vs[c2 * 32 + r]);
+        acc[q] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) {
+    const int pidx = tid + 256 * q;
+    const int c1 = pidx % g, c2 = pidx / g;
+    if (c2 < g && c1 < g) G[c2 * g + c1] = (c2 < gg && c1 < gg) ? acc[q] : zero;   // G[c1, c2] = v_c1^H v_c2
+  }
+  for (int idx = tid; idx < g * (g + 1); idx += 256) T[idx] = zero;
+  __syncthreads();
+  // T[i,i] = tau_i ; T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i] ; thread r owns row r
+  if (tid < g) {
+    const int r = tid;
+    cplx* Tr = T + r * (g + 1);
+    for (int i = 0; i < gg; ++i) {
+      const cplx t = tau2[((size_t)ch * n + s0 + i) * KT + k];
+      if (r < i) {
+        cplx s = zero;
+        for (int l = r; l < i; ++l) cfma(s, Tr[l], G[i * g + l]);
+        Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
+      } else if (r == i) {
+        Tr[i] = t;
+      }
+    }
+  }
+  __syncthreads();
+  cplx* out = Tall + ((size_t)ch * nblk + blk) * TG * TG;     // column-major, ld = TG
+  for (int idx = tid; idx < g * g; idx += 256) {
+    const int r = idx % g, c = idx / g;
+    out[c * TG + r] = T[r * (g + 1) + c];
+  }
+}
+
+// rows back to the reference's order: U[r, c] = Zb[pos[r], c]
+__global__ void __launch_bounds__(256) band_unpermute_kernel(const cplx* __restrict__ Zall, cplx* __restrict__ Uall,
+                                                             const int* __restrict__ pos, const int* __restrict__ halfflag,
+                                                             int c_lo, int n, Mask mask) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  if (!mask.on(b)) return;
+  if (c < c_lo && halfflag[b] != 0) return;
+  const cplx* src = Zall + (size_t)b * n * n + (size_t)c * n;
+  cplx* dst = Uall + (size_t)b * n * n + (size_t)c * n;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) dst[r] = src[pos[r]];
+}
+
+}  // namespace
+
+// ring fold: positions 0, L-1, 1, L-2, ... -> consecutive indices
+static std::vector<int> fold_positions(int L) {
+  std::vector<int> pos(L);
+  int lo = 0, hi = L - 1, idx = 0;
+  while (lo <= hi) {
+    pos[lo] = idx++;
+    if (hi != lo) pos[hi] = idx++;
+    ++lo; --hi;
+  }
+  return pos;
+}
+
+// Decide whether the band route applies and prepare its index tables.  nn / nnn: 0-based [dir * N + site].
+int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>& nnn) {
+  const int Lx = h->Lx, Ly = h->Ly, N = h->N, n = h->n;
+  h->band_b = 0;
+  std::vector<int> px = fold_positions(Lx), py = fold_positions(Ly);
+  std::vector<int> pos(n);
+  for (int y = 0; y < Ly; ++y)
+    for (int x = 0; x < Lx; ++x) {
+      const int i = y * Lx + x;
+      const int sidx = (Lx <= Ly) ? py[y] * Lx + px[x] : px[x] * Ly + py[y];   // short ring fastest
+      pos[i] = 2 * sidx;
+      pos[i + N] = 2 * sidx + 1;
+    }
+  int bw = 0;
+  for (int i = 0; i < N; ++i) {
+    for (int d = 0; d < 4; ++d) {
+      const int j = nn[d * N + i], j2 = nnn[d * N + i];
+      bw = std::max(bw, std::abs(pos[i] - pos[j]));
+      bw = std::max(bw, std::abs(pos[i] - pos[j2]));
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+      const int j = nn[dir * N + i];
+      bw = std::max(bw, std::abs(pos[i] - pos[j + N]));
+      bw = std::max(bw, std::abs(pos[j] - pos[i + N]));
+    }
+  }
+  bw = std::max(bw, 2);
+  // Opt-in (DWHMC_BAND=1): correct and parity-tested, but at L = 24 the bulge chase (95 ms per 64 chains)
+  // is still slower than the dense tridiagonalisation (83 ms); see DESIGN.md section 3.
+  int want = 0;
+  if (const char* e = getenv("DWHMC_BAND")) want = atoi(e);
+  const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
+  // the chase kernel keeps 20 block elements per thread in registers: b^2 <= 20 * 512
+  if (!want || 3 * bw > n || bw > 32 * RQ || (size_t)bw * bw > (size_t)EU * CT || smem > 225 * 1024) return DWHMC_OK;   // dense route
+  h->band_b = bw;
+  h->band_LD = 2 * bw;
+  h->band_KT = (n + bw - 1) / bw + 1;
+  // reflectors per block of the back-transformation: block height b + g - 1 a multiple of 64
+  int g = 64 * ((bw + 16 + 63) / 64) - bw + 1;
+  g = std::max(8, std::min(g, TG));
+  h->band_g = g;
+  // block list, application order: sweep groups last to first, steps ascending
+  std::vector<int> bs0, bk;
+  const int ngrp = (n - 1 + g - 1) / g;
+  for (int G = ngrp - 1; G >= 0; --G) {
+    const int s0 = G * g;
+    for (int k = 0;; ++k) {
+      const int r0 = s0 + 1 + k * bw;                 // first row of the first sweep of the group
+      const int len = n - r0;
+      if (len < 1 || (k > 0 && len < 2)) break;
+      bs0.push_back(s0);
+      bk.push_back(k);
+    }
+  }
+  h->band_blk_s0 = bs0;
+  h->band_blk_k = bk;
+  h->band_pos_host = pos;
+  return DWHMC_OK;
+}
+
+int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx* delta, Mask mask) {
+  const int n = h->n, N = h->N, B = h->B, LD = h->band_LD;
+  DW_CUDA(h, cudaMemsetAsync(h->A, 0, sizeof(cplx) * (size_t)n * LD * B, h->stream));
+  dim3 grid((N + 127) / 128, B);
+  band_scatter_kernel<<<grid, 128, 0, h->stream>>>(h->A, w, par3, delta, h->nn, h->nnn, h->band_pos, N, B, LD, mask);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
+// h->A (band) -> h->d, h->e, h->V (reflectors, column s = sweep s), h->band_tau
+int dw_band_chase(Handle* h, Mask mask) {
+  const int n = h->n, B = h->B, bw = h->band_b;
+  const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
+  static bool attr_set[64] = {false};
+  if (!attr_set[h->device & 63]) {
+    DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set[h->device & 63] = true;
+  }
+  int nsm = 0;
+  DW_CUDA(h, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+  int per_sm = 0;
+  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chase_kernel, CT, smem));
+  const int cap = nsm * per_sm;
+  if (cap < 1) { h->err = "dw_band_chase: kernel does not fit"; return DWHMC_E_CUDA; }
+  int P = std::max(1, std::min(4, cap / B));
+  if (const char* e = getenv("DWHMC_BAND_P")) P = std::max(1, std::min(atoi(e), cap));
+  const int per_launch = std::max(1, cap / P);                    // chains per launch
+  DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * (size_t)n * B, h->stream));
+  DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
+  for (int c0 = 0; c0 < B; c0 += per_launch) {
+    ChaseArgs a;
+    a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
+    a.n = n; a.b = bw; a.LD = h->band_LD; a.KT = h->band_KT; a.P = P; a.c0 = c0; a.mask = mask;
+    static long long* clk_dev = nullptr;
+    static const bool want_clk = getenv("DWHMC_BAND_CLK") != nullptr;
+    if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
+    a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
+    const int nch = std::min(per_launch, B - c0);
+    void* args[] = {&a};
+    DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(nch * P), dim3(CT), args, smem, h->stream));
+    h->launches++;
+    if (a.clk) {
+      long long c[8];
+      cudaStreamSynchronize(h->stream);
+      cudaMemcpy(c, a.clk, sizeof(c), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "chase phases (Mclk): wait %.1f A+larfg %.1f C %.1f Dload %.1f Dcomp %.1f Eload %.1f Ecomp %.1f publish %.1f\n",
+              c[0] / 1e6, c[1] / 1e6, c[2] / 1e6, c[3] / 1e6, c[4] / 1e6, c[5] / 1e6, c[6] / 1e6, c[7] / 1e6);
+    }
+  }
+  dim3 grid((n + 255) / 256, B);
+  band_de_kernel<<<grid, 256, 0, h->stream>>>(h->A, h->d, h->e, n, h->band_LD, mask);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
+// Zb (n x n complex, band row order, in h->A) <- Q2 Zb, then rows back to site order into U
+int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
+  const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
+  const int nblk = (int)h->band_blk_s0.size();
+  {
+    const size_t smem = sizeof(cplx) * ((size_t)g * g + (size_t)g * (g + 1));
+    static bool attr_set[64] = {false};
+    if (!attr_set[h->device & 63]) {
+      DW_CUDA(h, cudaFuncSetAttribute(band_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set[h->device & 63] = true;
+    }
+    dim3 grid(nblk, B);
+    band_tfactor_kernel<<<grid, 256, smem, h->stream>>>(h->V, h->band_tau, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev,
+                                                        n, bw, g, h->band_KT, nblk, mask);
+    DW_LAUNCH_CHECK(h);
+  }
+  const bool half = ph && h->ph_mode;
+  ZgemmArgs a;
+  a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
+  if (half) { a.skip_flag = h->halfflag; a.skip_cols = h->N; }
+  cplx* Z = h->A;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int s0 = h->band_blk_s0[blk], k = h->band_blk_k[blk];
+    const int gg = std::min(g, n - 1 - s0);
+    const int rlo = s0 + 1 + k * bw;
+    const int rows = std::min(n - rlo, bw + gg - 1);
+    if (rows <= 0 || gg <= 0) continue;
+    const cplx* Vb = h->V + (size_t)s0 * n + rlo;
+    cplx* Zb = Z + rlo;
+    // W1 (gg x n) = Vb^H Zb
+    a.M = gg; a.N = n; a.K = rows;
+    a.A[0] = Vb; a.lda = n; a.sA = (long long)n * n; a.opA = 1; a.stairA = bw;
+    a.Bm[0] = Zb; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
+    a.C = h->Wbt; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
+    a.alpha = 1.0; a.beta = 0.0;
+    DW_TRY(dw_zgemm(h, a));
+    // W2 = T W1
+    a.M = gg; a.N = n; a.K = gg; a.stairA = 0;
+    a.A[0] = h->band_T + (size_t)blk * TG * TG; a.lda = TG; a.sA = (long long)nblk * TG * TG; a.opA = 0;
+    a.Bm[0] = h->Wbt; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
+    a.C = h->Wbt2; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
+    a.alpha = 1.0; a.beta = 0.0;
+    DW_TRY(dw_zgemm(h, a));
+    // Zb -= Vb W2
+    a.M = rows; a.N = n; a.K = gg; a.stairA = bw;
+    a.A[0] = Vb; a.lda = n; a.sA = (long long)n * n; a.opA = 0;
+    a.Bm[0] = h->Wbt2; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
+    a.C = Zb; a.ldc = n; a.sC = (long long)n * n;
+    a.alpha = -1.0; a.beta = 1.0;
+    DW_TRY(dw_zgemm(h, a));
+  }
+  {
+    dim3 grid(n, B);
+    const int c_lo = half ? (h->N / 128) * 128 : 0;
+    band_unpermute_kernel<<<grid, 256, 0, h->stream>>>(Z, U, h->band_pos, h->halfflag, c_lo, n, mask);
+    DW_LAUNCH_CHECK(h);
+  }
+  return DWHMC_OK;
+}

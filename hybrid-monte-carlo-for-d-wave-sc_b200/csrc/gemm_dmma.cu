@@ -37,6 +37,7 @@ struct KArgs {
   Mask mask;
   const int* skip_flag;
   int skip_cols;
+  int stairA;
 };
 
 // two CTAs per SM whenever the tile's shared memory allows it (<= 128 registers per thread)
@@ -81,6 +82,7 @@ zgemm_dmma_kernel(KArgs g) {
         int idx = tid + i * NTHREADS;
         int m = idx % BM, kk = idx / BM;
         bool p = (m0 + m < g.M) && (k0 + kk < g.K);
+        if (g.stairA > 0) { const int df = (m0 + m) - (k0 + kk); p = p && df >= 0 && df < g.stairA; }
         const cplx* src = p ? A + (size_t)(k0 + kk) * g.lda + (m0 + m) : A;
         cp_async16(As + kk * (BM + 2) + m, src, p);
       }
@@ -90,6 +92,7 @@ zgemm_dmma_kernel(KArgs g) {
         int idx = tid + i * NTHREADS;
         int kk = idx % BK, m = idx / BK;
         bool p = (m0 + m < g.M) && (k0 + kk < g.K);
+        if (g.stairA > 0) { const int df = (k0 + kk) - (m0 + m); p = p && df >= 0 && df < g.stairA; }
         const cplx* src = p ? A + (size_t)(m0 + m) * g.lda + (k0 + kk) : A;
         cp_async16(As + m * (BK + 4) + kk, src, p);
       }
@@ -227,7 +230,7 @@ int launch(Handle* h, const ZgemmArgs& a) {
   g.lda = a.lda; g.ldb = a.ldb; g.ldc = a.ldc;
   g.sA = a.sA; g.sB = a.sB; g.sC = a.sC;
   g.C = a.C; g.alpha = a.alpha; g.beta = a.beta; g.lower = a.lower; g.mask = a.mask; g.b0 = a.b0;
-  g.skip_flag = a.skip_flag; g.skip_cols = a.skip_cols;
+  g.skip_flag = a.skip_flag; g.skip_cols = a.skip_cols; g.stairA = a.stairA;
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
   static int pad = -1;                  // DWHMC_GEMM_PAD=KB: extra dynamic smem (experiment: limit CTAs/SM)
   if (pad < 0) {

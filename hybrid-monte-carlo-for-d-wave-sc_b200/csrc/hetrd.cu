@@ -403,6 +403,111 @@ __global__ void __launch_bounds__(256) hemv_lower_kernel(const cplx* __restrict_
   }
 }
 
+// Register-path variant of hemv_lower_kernel (same tiles, same ypart slots, same result layout):
+// no shared-memory staging.  Warp w of the CTA owns columns 8w..8w+7 of the 64x64 tile, lane l the
+// rows l and l+32; the 16 elements of a lane are loaded straight into registers (16 independent
+// 16-byte requests per thread, each warp request one contiguous 512-byte segment) and used for both
+// passes.  The row pass accumulates in the lane; the column pass is reduced across the lanes with a
+// transposing butterfly (8 -> 4 -> 2 -> 1 values per lane, 9 complex exchanges instead of 40).
+// Diagonal tiles neither load nor use the strict upper triangle.
+__device__ __forceinline__ cplx shfl_xor_c(cplx v, int o) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
+}
+
+__global__ void __launch_bounds__(256, 2) hemv_reg_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
+                                                          cplx* __restrict__ ypart, int n, int B, int b0, int j,
+                                                          Mask mask) {
+  const int b = b0 + blockIdx.y;
+  if (!mask.on(b)) return;
+  __shared__ cplx red[8 * TS];
+  __shared__ cplx cs[TS];
+  const int q0 = j + 1, m = n - q0;
+  const int t = blockIdx.x;
+  int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((I + 1) * (I + 2) / 2 <= t) ++I;
+  while (I * (I + 1) / 2 > t) --I;
+  const int J = t - I * (I + 1) / 2;
+  const int R0 = I * TS, C0 = J * TS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool diag = (I == J);
+  const size_t mat = (size_t)b * n * n;
+  const int cl0 = warp * 8;                                  // first local column of this warp
+  const cplx* A = Aall + mat + (size_t)(q0 + C0 + cl0) * n + q0 + R0;
+  const cplx* v = Vall + mat + (size_t)j * n + q0;
+  const unsigned long long pol = policy_evict_first();
+  const cplx zero = make_double2(0.0, 0.0);
+  cplx a[2][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int rl = lane + 32 * hh, cl = cl0 + c;
+      const bool p = (R0 + rl < m) && (C0 + cl < m) && (!diag || rl >= cl);
+      a[hh][c] = p ? ld_keep(A + (size_t)c * n + rl, pol) : zero;
+    }
+  cplx vr[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) vr[hh] = (R0 + lane + 32 * hh < m) ? v[R0 + lane + 32 * hh] : zero;
+  cplx accR[2] = {zero, zero};
+  cplx accC[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int cl = cl0 + c;
+    const cplx vc = (C0 + cl < m) ? v[C0 + cl] : zero;
+    cplx s = zero;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const cplx x = a[hh][c];
+      cfma(accR[hh], x, vc);
+      const bool ondiag = diag && (lane + 32 * hh == cl);
+      if (!ondiag) cfmac(s, x, vr[hh]);
+    }
+    accC[c] = s;
+  }
+  // transposing butterfly: afterwards the lanes with lane >> 2 == c hold the sum of column c
+  cplx r4[4], r2[2], r1;
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const cplx send = up ? accC[k] : accC[k + 4];
+      const cplx keep = up ? accC[k + 4] : accC[k];
+      r4[k] = cadd(keep, shfl_xor_c(send, 16));
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const cplx send = up ? r4[k] : r4[k + 2];
+      const cplx keep = up ? r4[k + 2] : r4[k];
+      r2[k] = cadd(keep, shfl_xor_c(send, 8));
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    const cplx send = up ? r2[0] : r2[1];
+    const cplx keep = up ? r2[1] : r2[0];
+    r1 = cadd(keep, shfl_xor_c(send, 4));
+  }
+  r1 = cadd(r1, shfl_xor_c(r1, 2));
+  r1 = cadd(r1, shfl_xor_c(r1, 1));
+  if ((lane & 3) == 0) cs[cl0 + (lane >> 2)] = r1;
+  red[warp * TS + lane] = accR[0];
+  red[warp * TS + lane + 32] = accR[1];
+  __syncthreads();
+  if (tid < TS) {
+    cplx sum = red[tid];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum = cadd(sum, red[w * TS + tid]);
+    if (diag) sum = cadd(sum, cs[tid]);
+    if (R0 + tid < m) ypart[((size_t)(diag ? I : J) * B + b) * n + q0 + R0 + tid] = sum;
+  } else if (tid < 2 * TS && !diag) {
+    const int x = tid - TS;
+    if (C0 + x < m) ypart[((size_t)I * B + b) * n + q0 + C0 + x] = cs[x];
+  }
+}
+
 __global__ void lastd_kernel(const cplx* __restrict__ A, double* __restrict__ d, int n, int B, Mask mask) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B || !mask.on(b)) return;
@@ -470,7 +575,8 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
         col_done(g);
         dim3 grid(nt * (nt + 1) / 2, gB[g]);
         if (h->profiling >= 2) cudaEventRecord(h->ev_begin, lp[g]);
-        hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        if (h->hemv_variant == 0) hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        else hemv_reg_kernel<<<grid, 256, 0, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
         DW_LAUNCH_CHECK(h);
         if (h->profiling >= 2) {
           cudaEventRecord(h->ev_end, lp[g]);

@@ -118,9 +118,18 @@ struct Handle {
   int* nrot = nullptr;          // [n*B]
   double* rho = nullptr;        // [n*B]
   int* status = nullptr;        // [4] device: [0] leaf failures, [1] secular non-convergence
+  // band route (band.cu): half-bandwidth of the BdG matrix in the folded site order; 0 = dense route
+  int band_b = 0, band_LD = 0, band_KT = 0, band_g = 0;
+  std::vector<int> band_pos_host, band_blk_s0, band_blk_k;
+  int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
+  int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase)
+  cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
+  cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
+  int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
   int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
   // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
   // upper half of the spectrum are back-transformed, the rest are their conjugate partners
+  int hemv_variant = 1;         // 1: register-path hemv (default); 0: shared-memory staged (env DWHMC_HEMV)
   int ph_mode = 1;              // env DWHMC_PH=0 switches the shortcut off
   int* halfflag = nullptr;      // device [B]: 1 = this chain's last eigensolve used the shortcut
   long long launches = 0;
@@ -169,8 +178,15 @@ int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph);
 // backtransform.cu: U <- Q U (flagged chains: upper-half columns only, then the partner columns)
 int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
 int dw_ph_mirror(Handle* h, double* E, cplx* U, Mask mask);
-// A (assembled, destroyed) -> E, U.  ph: the matrix is a BdG matrix assembled by dw_assemble.
+// A (assembled, destroyed) -> E, U.  ph: the matrix is the BdG matrix assembled by dw_assemble_for_solve
+// (band storage when the band route is active); otherwise a dense Hermitian matrix in h->A.
 int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph);
+int dw_assemble_for_solve(Handle* h, const double* w, const double* par3, const cplx* delta, Mask mask);
+// band.cu
+int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>& nnn);
+int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx* delta, Mask mask);
+int dw_band_chase(Handle* h, Mask mask);
+int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
 
 // generic batched complex GEMM on FP64 tensor cores (gemm_dmma.cu)
 // C = beta*C + alpha * sum_seg opA(A_seg) * opB(B_seg);  opX: 0 = N, 1 = C (conjugate transpose)
@@ -187,6 +203,8 @@ struct ZgemmArgs {
   int batch;
   Mask mask;
   int b0 = 0;                  // first chain of the launch (chain groups)
+  int stairA = 0;              // > 0: the A operand is a staircase block: entry (row r, column c) of the
+                               //   source is used only if 0 <= r - c < stairA (band.cu block reflectors)
   const int* skip_flag = nullptr;  // device [B] or null: chains with flag != 0 skip the column tiles that
   int skip_cols = 0;               //   lie entirely below column skip_cols
   cudaStream_t stream = nullptr;   // nullptr = the handle's stream

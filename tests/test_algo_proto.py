@@ -19,3 +19,32 @@ def test_blocked_hetrd_backtransform(n, nb):
     U = backtransform(V, larft_blocks(V, tau, P2, nb), Z, nb)
     assert np.max(np.abs(U.conj().T @ U - np.eye(n))) < 1e-12
     assert np.max(np.abs(A @ U - U * w)) < 1e-11
+
+
+def test_band_route_prototype_matches_lapack():
+    """tests/algo_proto_band.py (the formulas of csrc/band.cu): fold ordering -> band matrix of
+    half-bandwidth 4L+4; bulge chase -> tridiagonal with the same spectrum; blocked staircase
+    back-transformation -> eigenvectors."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import dwhmc_oracle as orc
+    import scipy.linalg as sl
+    import algo_proto_band as apb
+    for L, g in ((6, 5), (8, 29)):
+        p = orc.ModelParameters(L, L, 1.0, -0.35, -1.08, 1.0, 0.05, 20.0, 0.8, 1.0)
+        _, st, c = orc.make_chain(p, 3)
+        H = orc.full_hermitian(c)
+        n = 2 * L * L
+        pos = apb.band_positions(L, L)
+        Hp = np.zeros_like(H)
+        Hp[np.ix_(pos, pos)] = H
+        i, j = np.nonzero(Hp)
+        b = int(np.max(np.abs(i - j)))
+        assert b == 4 * L + 4
+        d, e, V, TAU = apb.chase_band(Hp, b)
+        w, Z = sl.eigh_tridiagonal(d, e)
+        assert np.max(np.abs(w - c.E_n)) <= 1e-12 * np.max(np.abs(c.E_n))
+        U = apb.backtransform_blocked(Z, V, TAU, b, g)
+        assert np.max(np.abs(Hp @ U - U * w)) <= 1e-12 * np.max(np.abs(w))
+        assert np.max(np.abs(U.conj().T @ U - np.eye(n))) <= 1e-12

@@ -294,6 +294,44 @@ def test_particle_hole_shortcut_and_fallback(dw, monkeypatch):
     cb.close()
 
 
+def test_band_route_matches_dense_route(dw, monkeypatch):
+    """DWHMC_BAND=1: BdG matrix assembled straight into band storage (folded site order, half-bandwidth
+    4L+4), bulge-chased to tridiagonal form, block-reflector back-transformation.  Same spectrum,
+    forces, observables and trajectories as the dense route and the oracle."""
+    L, B, Nt = 8, 3, 3
+    betas = [2.0, 20.0, 200.0]
+    monkeypatch.setenv("DWHMC_BAND", "1")
+    cb, ps, sts, cs = make_batch(dw, L, betas, 0.05, 1300)
+    monkeypatch.delenv("DWHMC_BAND")
+    n = 2 * L * L
+    E, U = cb.get_eigenvalues(), cb.get_eigenvectors()
+    for b in range(B):
+        Hf = orc.full_hermitian(cs[b]); Ub = U[b].T
+        nrm = np.max(np.abs(cs[b].E_n))
+        assert np.max(np.abs(E[b] - cs[b].E_n)) <= 1e-12 * nrm
+        assert np.max(np.abs(Hf @ Ub - Ub * E[b])) <= 1e-12 * nrm
+        assert np.max(np.abs(Ub.conj().T @ Ub - np.eye(n))) <= 1e-12
+    d, e = cb.debug_tridiagonalize()
+    import scipy.linalg as sl
+    for b in range(B):
+        wt = sl.eigh_tridiagonal(d[b], e[b], eigvals_only=True)
+        assert np.max(np.abs(wt - cs[b].E_n)) <= 1e-12 * np.max(np.abs(cs[b].E_n))
+    cb.compute_forces()
+    F = cb.get_forces()
+    dt = np.array([0.5 * orc.calc_optimal_dt(p.beta, p.J, p.mass, Nt) for p in ps])
+    pi0 = np.stack([orc.draw_momentum(ps[b], np.random.default_rng(50 + b)) for b in range(B)])
+    u = np.random.default_rng(51).random(B)
+    acc, dH = cb.hmc_sweep(Nt, dt, pi0=pi0, uniforms=u)
+    for b in range(B):
+        orc.compute_forces(cs[b], ps[b], sts[b])
+        assert rel(F[b].T, cs[b].forces) <= RTOL
+        a_r, dH_r, Ho, _ = orc.hmc_sweep(cs[b], ps[b], sts[b], Nt=Nt, dt=float(dt[b]), pi0=pi0[b], uniform=float(u[b]),
+                                         return_energies=True)
+        assert abs(dH[b] - dH_r) <= RTOL * max(abs(Ho), 1.0)
+        assert bool(acc[b]) == a_r
+    cb.close()
+
+
 def test_debug_stages(dw):
     import scipy.linalg as sl
     B, L = 2, 6
