@@ -12,6 +12,9 @@
 // tests/algo_proto.py.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "dwhmc.h"
 #include "internal.h"
 
@@ -115,6 +118,7 @@ struct ColArgs {
   cplx* A; cplx* V; cplx* W; cplx* ypart; cplx* P1; cplx* P2; cplx* tau;
   double* d; double* e;
   int n, B, b0, j, j0, finish_prev, make_ref;
+  int skip_dots;      // the products W^H v, V^H v are computed by the dot CTAs of the hemv launch instead
   Mask mask;
 };
 
@@ -279,7 +283,7 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
     const int nw = CT / 32;
     const int r0 = max(lo, j + 1);
     const int ndots = 2 * i;
-    if (warp < ndots) {
+    if (warp < ndots && !g.skip_dots) {
       const cplx* src[8];
       cplx acc[8];
 #pragma unroll
@@ -414,11 +418,63 @@ __device__ __forceinline__ cplx shfl_xor_c(cplx v, int o) {
   return make_double2(__shfl_xor_sync(0xffffffffu, v.x, o), __shfl_xor_sync(0xffffffffu, v.y, o));
 }
 
+// The last CC CTAs of each chain's row of the grid are "dot CTAs": they compute this column's products
+// W_panel^H v and V_panel^H v (needed only by the next column step) while the tile CTAs stream the
+// trailing matrix, which takes one pass over the panel off the critical path of the column step.
 __global__ void __launch_bounds__(256, 2) hemv_reg_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
                                                           cplx* __restrict__ ypart, int n, int B, int b0, int j,
-                                                          Mask mask) {
+                                                          Mask mask, const cplx* __restrict__ Wall, cplx* __restrict__ P1,
+                                                          cplx* __restrict__ P2, int j0, int ntiles) {
   const int b = b0 + blockIdx.y;
   if (!mask.on(b)) return;
+  if ((int)blockIdx.x >= ntiles) {
+    const int rank = blockIdx.x - ntiles;
+    const int i = j - j0, ndots = 2 * i;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = 8;
+    if (warp >= ndots) return;
+    const int chunk = (n - j + CC - 1) / CC;            // same row slices as the column-step cluster
+    const int lo = j + rank * chunk, hi = min(n, lo + chunk);
+    const int r0 = max(lo, j + 1);
+    const size_t mat = (size_t)b * n * n;
+    const cplx* V = Vall + mat;
+    const cplx* W = Wall + mat;
+    const cplx* v = V + (size_t)j * n;
+    const unsigned long long pol = policy_evict_last();
+    const cplx* src[8];
+    cplx acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int q = min(warp + nw * t, ndots - 1);
+      src[t] = ((q & 1) ? V : W) + (size_t)(j0 + (q >> 1)) * n;
+      acc[t] = make_double2(0.0, 0.0);
+    }
+    for (int r = r0 + lane; r < hi; r += 64) {
+      const bool two = r + 32 < hi;
+      const cplx v0 = v[r];
+      const cplx v1 = two ? v[r + 32] : make_double2(0.0, 0.0);
+      cplx x0[8], x1[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        x0[t] = ld_keep(src[t] + r, pol);
+        x1[t] = two ? ld_keep(src[t] + r + 32, pol) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        cfmac(acc[t], x0[t], v0);
+        cfmac(acc[t], x1[t], v1);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int q = warp + nw * t;
+      const cplx sum = warp_sum(acc[t]);
+      if (lane == 0 && q < ndots) {
+        if (q & 1) P2[((size_t)b * CC + rank) * DW_NB + (q >> 1)] = sum;
+        else P1[((size_t)b * CC + rank) * DW_NB + (q >> 1)] = sum;
+      }
+    }
+    return;
+  }
   __shared__ cplx red[8 * TS];
   __shared__ cplx cs[TS];
   const int q0 = j + 1, m = n - q0;
@@ -508,6 +564,179 @@ __global__ void __launch_bounds__(256, 2) hemv_reg_kernel(const cplx* __restrict
   }
 }
 
+// Persistent, warp-autonomous variant (hemv_variant 2).  Every warp is an independent worker with its
+// own list of (tile, chain) items and its own cp.async ring in shared memory: a stage is one 64 x 8
+// sub-tile (8 KB) plus the 8 entries of v on its columns; each lane copies exactly the 16 elements it
+// will consume (rows l, l+32 of the 8 columns), so a stage needs no block barrier, and loads stay in
+// flight across tile boundaries.  A warp walks the 8 sub-tiles of a tile, keeps the row sums in
+// registers, reduces the column sums with the transposing butterfly, and writes the tile's results
+// alone.  One CTA per SM; its shared memory is sized to leave room for the column-step CTAs of the
+// other chain group.
+constexpr int HW_WARPS = 7;
+constexpr int HW_DEPTH = 3;
+constexpr int HW_STAGE = 64 * 8 + 8;                           // cplx per stage: sub-tile + v on its columns
+constexpr int HW_PER_WARP = HW_DEPTH * HW_STAGE + 2 * 64 + 64;  // + v on the rows (2 items) + column sums
+constexpr size_t HW_SMEM = sizeof(cplx) * HW_WARPS * HW_PER_WARP;
+
+__device__ __forceinline__ void cp_async16_plain(void* smem, const void* gmem, bool pred) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+
+__device__ __forceinline__ void tile_decode(int t, int& I, int& J) {
+  I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((I + 1) * (I + 2) / 2 <= t) ++I;
+  while (I * (I + 1) / 2 > t) --I;
+  J = t - I * (I + 1) / 2;
+}
+
+__global__ void __launch_bounds__(HW_WARPS * 32, 1) hemv_warp_kernel(const cplx* __restrict__ Aall,
+                                                                     const cplx* __restrict__ Vall,
+                                                                     cplx* __restrict__ ypart, int n, int B, int b0,
+                                                                     int nb, int j, int ntiles, Mask mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cplx* ring = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * HW_PER_WARP;
+  cplx* vrb = ring + HW_DEPTH * HW_STAGE;       // [2][64]
+  cplx* cs = vrb + 2 * 64;                      // [64]
+  const int q0 = j + 1, m = n - q0;
+  const int gw = blockIdx.x * HW_WARPS + warp, GW = gridDim.x * HW_WARPS;
+  const int nitems = ntiles * nb;
+  const cplx zero = make_double2(0.0, 0.0);
+
+  // issue cursor
+  int it_i = gw, sub_i = 0, I_i = 0, J_i = 0, b_i = 0, cnt_i = 0;
+  bool on_i = false;
+  auto setup_issue = [&]() {
+    while (it_i < nitems) {
+      b_i = b0 + it_i / ntiles;
+      if (mask.on(b_i)) { tile_decode(it_i % ntiles, I_i, J_i); on_i = true; return; }
+      it_i += GW;
+    }
+    on_i = false;
+  };
+  auto issue = [&](int stage) {
+    if (on_i) {
+      const int R0 = I_i * TS, C0 = J_i * TS, cl0 = sub_i * 8;
+      const bool diag = (I_i == J_i);
+      const size_t mat = (size_t)b_i * n * n;
+      const cplx* A = Aall + mat + (size_t)(q0 + C0 + cl0) * n + q0 + R0;
+      const cplx* v = Vall + mat + (size_t)j * n + q0;
+      cplx* st = ring + stage * HW_STAGE;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rl = lane + 32 * hh, cl = cl0 + c;
+          const bool p = (R0 + rl < m) && (C0 + cl < m) && (!diag || rl >= cl);
+          cp_async16_plain(st + c * 64 + rl, p ? A + (size_t)c * n + rl : A, p);
+        }
+      if (lane < 8) {
+        const bool p = C0 + cl0 + lane < m;
+        cp_async16_plain(st + 512 + lane, p ? v + C0 + cl0 + lane : v, p);
+      }
+      if (sub_i == 0) {
+        cplx* vb = vrb + (cnt_i & 1) * 64;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int rl = lane + 32 * hh;
+          const bool p = R0 + rl < m;
+          cp_async16_plain(vb + rl, p ? v + R0 + rl : v, p);
+        }
+      }
+      if (++sub_i == 8) { sub_i = 0; ++cnt_i; it_i += GW; setup_issue(); }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  setup_issue();
+#pragma unroll
+  for (int s = 0; s < HW_DEPTH - 1; ++s) issue(s);
+
+  // consume cursor
+  int it_c = gw, cnt_c = 0, stage = 0;
+  while (it_c < nitems) {
+    const int b = b0 + it_c / ntiles;
+    if (!mask.on(b)) { it_c += GW; continue; }
+    int I, J;
+    tile_decode(it_c % ntiles, I, J);
+    const int R0 = I * TS, C0 = J * TS;
+    const bool diag = (I == J);
+    cplx accR[2] = {zero, zero};
+    const cplx* vb = vrb + (cnt_c & 1) * 64;
+    for (int sub = 0; sub < 8; ++sub) {
+      issue((stage + HW_DEPTH - 1) % HW_DEPTH);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(HW_DEPTH - 1));
+      __syncwarp();
+      const cplx* st = ring + stage * HW_STAGE;
+      const cplx vr0 = vb[lane], vr1 = vb[lane + 32];
+      const int cl0 = sub * 8;
+      cplx accC[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const cplx vc = st[512 + c];
+        const cplx x0 = st[c * 64 + lane], x1 = st[c * 64 + lane + 32];
+        cfma(accR[0], x0, vc);
+        cfma(accR[1], x1, vc);
+        cplx sacc = zero;
+        if (!(diag && lane == cl0 + c)) cfmac(sacc, x0, vr0);
+        if (!(diag && lane + 32 == cl0 + c)) cfmac(sacc, x1, vr1);
+        accC[c] = sacc;
+      }
+      cplx r4[4], r2[2], r1;
+      {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const cplx send = up ? accC[k] : accC[k + 4];
+          const cplx keep = up ? accC[k + 4] : accC[k];
+          r4[k] = cadd(keep, shfl_xor_c(send, 16));
+        }
+      }
+      {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const cplx send = up ? r4[k] : r4[k + 2];
+          const cplx keep = up ? r4[k + 2] : r4[k];
+          r2[k] = cadd(keep, shfl_xor_c(send, 8));
+        }
+      }
+      {
+        const bool up = (lane & 4) != 0;
+        const cplx send = up ? r2[0] : r2[1];
+        const cplx keep = up ? r2[1] : r2[0];
+        r1 = cadd(keep, shfl_xor_c(send, 4));
+      }
+      r1 = cadd(r1, shfl_xor_c(r1, 2));
+      r1 = cadd(r1, shfl_xor_c(r1, 1));
+      if ((lane & 3) == 0) cs[cl0 + (lane >> 2)] = r1;
+      __syncwarp();
+      stage = (stage + 1) % HW_DEPTH;
+    }
+    // results of the tile
+    if (diag) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int x = lane + 32 * hh;
+        if (R0 + x < m) ypart[((size_t)I * B + b) * n + q0 + R0 + x] = cadd(accR[hh], cs[x]);
+      }
+    } else {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int x = lane + 32 * hh;
+        if (R0 + x < m) ypart[((size_t)J * B + b) * n + q0 + R0 + x] = accR[hh];
+        if (C0 + x < m) ypart[((size_t)I * B + b) * n + q0 + C0 + x] = cs[x];
+      }
+    }
+    __syncwarp();
+    ++cnt_c;
+    it_c += GW;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
 __global__ void lastd_kernel(const cplx* __restrict__ A, double* __restrict__ d, int n, int B, Mask mask) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B || !mask.on(b)) return;
@@ -528,6 +757,7 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
   if (!attr_set[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(colstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     DW_CUDA(h, cudaFuncSetAttribute(hemv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEMV_SMEM));
+    DW_CUDA(h, cudaFuncSetAttribute(hemv_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HW_SMEM));
     attr_set[h->device & 63] = true;
   }
   if (col_smem > 200 * 1024) { h->err = "dw_hetrd: matrix too large for the column-step kernel"; return DWHMC_E_BADARG; }
@@ -558,6 +788,9 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
   auto col_done = [&](int g) {
     if (G > 1) { cudaEventRecord(h->ev_col[g], hp[g]); cudaStreamWaitEvent(lp[g], h->ev_col[g], 0); }
   };
+  static const bool skip_hemv = getenv("DWHMC_SKIP_HEMV") != nullptr;   // timing experiments only (results invalid)
+  static const bool skip_col = getenv("DWHMC_SKIP_COL") != nullptr;
+  static const bool skip_her2k = getenv("DWHMC_SKIP_HER2K") != nullptr;
   ColArgs ca;
   ca.A = h->A; ca.V = h->V; ca.W = W; ca.ypart = h->ypart; ca.P1 = h->P1; ca.P2 = h->P2; ca.tau = h->tau;
   ca.d = h->d; ca.e = h->e; ca.n = n; ca.B = B; ca.mask = mask;
@@ -570,13 +803,23 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       const int nt = (m + TS - 1) / TS;
       for (int g = 0; g < G; ++g) {
         ca.j = j; ca.finish_prev = (i > 0); ca.make_ref = 1; ca.b0 = gb0[g];
-        colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
+        static const bool dots_in_hemv = getenv("DWHMC_DOTS_IN_HEMV") != nullptr;   // experiment: no gain measured
+        ca.skip_dots = (h->hemv_variant == 1 && dots_in_hemv) ? 1 : 0;
+        if (!skip_col) colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
         DW_LAUNCH_CHECK(h);
         col_done(g);
         dim3 grid(nt * (nt + 1) / 2, gB[g]);
+        if (skip_hemv) { bulk_done(g); continue; }
         if (h->profiling >= 2) cudaEventRecord(h->ev_begin, lp[g]);
-        if (h->hemv_variant == 0) hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
-        else hemv_reg_kernel<<<grid, 256, 0, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        if (h->hemv_variant == 2) {
+          const int items = (int)grid.x * gB[g];
+          const int ctas = std::min(h->nsm, (items + HW_WARPS - 1) / HW_WARPS);
+          hemv_warp_kernel<<<ctas, HW_WARPS * 32, HW_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], gB[g], j, (int)grid.x, mask);
+        } else if (h->hemv_variant == 0) hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
+        else {
+          dim3 grid2(grid.x + (ca.skip_dots ? CC : 0), gB[g]);
+          hemv_reg_kernel<<<grid2, 256, 0, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask, W, h->P1, h->P2, j0, (int)grid.x);
+        }
         DW_LAUNCH_CHECK(h);
         if (h->profiling >= 2) {
           cudaEventRecord(h->ev_end, lp[g]);
@@ -590,7 +833,7 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
     }
     const int j1 = j0 + pn;
     for (int g = 0; g < G; ++g) {
-      ca.j = j1; ca.finish_prev = 1; ca.make_ref = 0; ca.b0 = gb0[g];
+      ca.j = j1; ca.finish_prev = 1; ca.make_ref = 0; ca.b0 = gb0[g]; ca.skip_dots = 0;
       colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
       DW_LAUNCH_CHECK(h);
       col_done(g);
@@ -604,7 +847,7 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       a.C = h->A + (size_t)j1 * n + j1;
       a.alpha = -1.0; a.beta = 1.0; a.opA = 0; a.opB = 1; a.lower = 1; a.batch = gB[g]; a.mask = mask;
       a.b0 = gb0[g]; a.stream = lp[g];
-      DW_TRY(dw_zgemm(h, a));
+      if (!skip_her2k) DW_TRY(dw_zgemm(h, a));
       bulk_done(g);
     }
   }

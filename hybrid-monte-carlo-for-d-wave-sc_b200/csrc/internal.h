@@ -129,6 +129,7 @@ struct Handle {
   int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
   // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
   // upper half of the spectrum are back-transformed, the rest are their conjugate partners
+  int nsm = 148;                // SMs of the device
   int hemv_variant = 1;         // 1: register-path hemv (default); 0: shared-memory staged (env DWHMC_HEMV)
   int ph_mode = 1;              // env DWHMC_PH=0 switches the shortcut off
   int* halfflag = nullptr;      // device [B]: 1 = this chain's last eigensolve used the shortcut
