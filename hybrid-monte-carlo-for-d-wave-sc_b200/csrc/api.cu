@@ -215,6 +215,8 @@ int dwhmc_destroy(dwhmc_handle hh) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->tr_work) cudaFree(h->tr_work);
+  if (h->tr_out) cudaFree(h->tr_out);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_begin) cudaEventDestroy(h->ev_begin);
@@ -339,6 +341,48 @@ int dwhmc_measure_observables(dwhmc_handle hh, double* out) {
   if (!h->params_set) { h->err = "dwhmc_measure_observables: parameters not set"; return DWHMC_E_STATE; }
   DW_TRY(dw_observables(h, h->obs_dev));
   return d2h(h, out, h->obs_dev, sizeof(double) * DWHMC_NOBS * h->B);
+}
+
+int dwhmc_measure_transport(dwhmc_handle hh, double eta, const double* omega_grid, int n_omega, const double* dos_grid,
+                            int n_dos, double* scalars, double* sigma, double* dos, double* dos_AN, double* A_k0) {
+  H_ENTER(hh);
+  if (!h->params_set) { h->err = "dwhmc_measure_transport: parameters not set"; return DWHMC_E_STATE; }
+  if (h->pending) { h->err = "dwhmc_measure_transport: a trajectory proposal is pending (commit first)"; return DWHMC_E_STATE; }
+  if (!(eta > 0.0) || n_omega < 0 || n_dos < 0 || (n_omega > 0 && !omega_grid) || (n_dos > 0 && !dos_grid))
+    BADARG("dwhmc_measure_transport: need eta > 0 and the frequency grids");
+  const int B = h->B, N = h->N;
+  const size_t wc = dw_transport_work_count(h, n_omega);
+  if (wc > h->tr_work_count) {
+    if (h->tr_work) cudaFree(h->tr_work);
+    h->tr_work = nullptr; h->tr_work_count = 0;
+    DW_CUDA(h, cudaMalloc(&h->tr_work, sizeof(double) * wc));
+    h->tr_work_count = wc;
+  }
+  const size_t oc = (size_t)2 * B + (size_t)n_omega * B + (size_t)2 * n_dos * B + (size_t)N * B + n_omega + n_dos + 8;
+  if (oc > h->tr_out_count) {
+    if (h->tr_out) cudaFree(h->tr_out);
+    h->tr_out = nullptr; h->tr_out_count = 0;
+    DW_CUDA(h, cudaMalloc(&h->tr_out, sizeof(double) * oc));
+    h->tr_out_count = oc;
+  }
+  double* scal_d = h->tr_out;
+  double* sigma_d = scal_d + (size_t)2 * B;
+  double* dos_d = sigma_d + (size_t)n_omega * B;
+  double* dosAN_d = dos_d + (size_t)n_dos * B;
+  double* ak_d = dosAN_d + (size_t)n_dos * B;
+  double* omega_d = ak_d + (size_t)N * B;
+  double* grid_d = omega_d + n_omega;
+  if (n_omega > 0) DW_TRY(h2d(h, omega_d, omega_grid, sizeof(double) * n_omega));
+  if (n_dos > 0) DW_TRY(h2d(h, grid_d, dos_grid, sizeof(double) * n_dos));
+  DW_TRY(dw_transport(h, eta, omega_d, n_omega, grid_d, n_dos, scal_d, sigma_d, dos_d, dosAN_d, ak_d, h->tr_work,
+                      h->tr_work_count));
+  if (scalars) DW_TRY(d2h(h, scalars, scal_d, sizeof(double) * 2 * B));
+  if (sigma && n_omega > 0) DW_TRY(d2h(h, sigma, sigma_d, sizeof(double) * (size_t)n_omega * B));
+  if (dos && n_dos > 0) DW_TRY(d2h(h, dos, dos_d, sizeof(double) * (size_t)n_dos * B));
+  if (dos_AN && n_dos > 0) DW_TRY(d2h(h, dos_AN, dosAN_d, sizeof(double) * (size_t)n_dos * B));
+  if (A_k0) DW_TRY(d2h(h, A_k0, ak_d, sizeof(double) * (size_t)N * B));
+  DW_CUDA(h, cudaStreamSynchronize(h->stream));
+  return DWHMC_OK;
 }
 
 int dwhmc_get_H(dwhmc_handle hh, double* out) {

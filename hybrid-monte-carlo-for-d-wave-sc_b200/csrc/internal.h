@@ -126,6 +126,9 @@ struct Handle {
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
   cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
+  // transport / spectra workspace (transport.cu), allocated on first use
+  double* tr_work = nullptr; size_t tr_work_count = 0;
+  double* tr_out = nullptr; size_t tr_out_count = 0;     // scal | sigma | dos | dosAN | ak | omega | dosgrid
   int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
   // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
   // upper half of the spectrum are back-transformed, the rest are their conjugate partners
@@ -211,6 +214,11 @@ struct ZgemmArgs {
   cudaStream_t stream = nullptr;   // nullptr = the handle's stream
 };
 int dw_zgemm(Handle* h, const ZgemmArgs& a);
+
+// transport.cu
+int dw_transport(Handle* h, double eta, const double* omega_dev, int nw, const double* dosgrid_dev, int nd,
+                 double* scal, double* sigma, double* dos, double* dosAN, double* ak, double* work, size_t work_count);
+size_t dw_transport_work_count(const Handle* h, int nw);
 
 // force.cu ---------------------------------------------------------------------------
 // bond correlators of (U, E) -> h->Pbond, h->fermi; then F = -(beta/2J)(Delta - J P) -> h->force.

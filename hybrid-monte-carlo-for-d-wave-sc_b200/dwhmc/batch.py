@@ -44,6 +44,12 @@ def calc_optimal_dt(beta: float, J: float, mass: float, Nt: int) -> float:
     return T / (2 * Nt)
 
 
+def julia_range(start: float, step: float, stop: float) -> np.ndarray:
+    """collect(start:step:stop) for Float64 steps (the grids of src/Observables.jl:402, :433)."""
+    nsteps = int(math.floor((stop - start) / step + 1e-10)) + 1
+    return np.ascontiguousarray(start + step * np.arange(max(nsteps, 0), dtype=np.float64))
+
+
 def _vec(x, B):
     a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (B,)))
     return a
@@ -141,6 +147,21 @@ class ChainBatch:
         out = np.empty((self.B, _lib.NOBS))
         check(lib.dwhmc_measure_observables(self._h, dptr(out)), self._h)
         return out
+
+    def measure_transport_and_spectra(self, eta: float, d_omega: float, omega_max: float):
+        """measure_transport_and_spectra (src/Observables.jl:314-526) for every chain.  Returns a dict with
+        superfluid_stiffness[B], dc_conductivity[B], omega_grid[n_w], optical_conductivity[B, n_w],
+        dos_omega_grid[n_d], dos[B, n_d], dos_AN[B, n_d], A_k_w0[B, Lx, Ly]."""
+        og = julia_range(eta, d_omega, omega_max)
+        dg = julia_range(-omega_max, d_omega, omega_max)
+        B = self.B
+        scal = np.empty((B, 2)); sig = np.empty((B, len(og))); dos = np.empty((B, len(dg))); dan = np.empty((B, len(dg)))
+        ak = np.empty((B, self.Ly, self.Lx))
+        check(lib.dwhmc_measure_transport(self._h, float(eta), dptr(og), len(og), dptr(dg), len(dg), dptr(scal), dptr(sig),
+                                          dptr(dos), dptr(dan), dptr(ak)), self._h)
+        return dict(superfluid_stiffness=scal[:, 0].copy(), dc_conductivity=scal[:, 1].copy(), omega_grid=og,
+                    optical_conductivity=sig, dos_omega_grid=dg, dos=dos, dos_AN=dan,
+                    A_k_w0=np.ascontiguousarray(ak.transpose(0, 2, 1)))
 
     # ---- cache getters
     def get_H(self):

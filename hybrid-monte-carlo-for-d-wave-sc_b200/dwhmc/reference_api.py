@@ -21,6 +21,9 @@ import numpy as np
 from .batch import ChainBatch, calc_optimal_dt, neighbour_tables, OBS_NAMES  # noqa: F401
 
 ObservablesResult = namedtuple("ObservablesResult", OBS_NAMES)   # src/Observables.jl:70-80
+SpectrumResult = namedtuple("SpectrumResult", ("superfluid_stiffness", "dc_conductivity", "omega_grid",
+                                               "optical_conductivity", "dos_omega_grid", "dos", "dos_AN",
+                                               "A_k_w0"))                 # src/Observables.jl:293-311
 
 
 @dataclass
@@ -184,3 +187,19 @@ def measure_observables(cache: ComputeCache, p: ModelParameters, state: Simulati
     cache._sync_params(p)
     _push_field(cache, state)
     return ObservablesResult(*cache.batch.measure_observables()[0])
+
+
+def build_current_operator(cache: ComputeCache, p: ModelParameters) -> None:
+    """src/Observables.jl:237-283.  The current operator lives in the kernels (a 6-point gather with
+    the handle's neighbour tables and the chain's t, t'); nothing to precompute on the host."""
+    cache._sync_params(p)
+
+
+def measure_transport_and_spectra(cache: ComputeCache, p: ModelParameters) -> SpectrumResult:
+    """src/Observables.jl:314-526: uses cache.E_n, cache.U and the fermi_factors of the last
+    compute_forces / measure_observables call, like the reference (:321)."""
+    cache._sync_params(p)
+    r = cache.batch.measure_transport_and_spectra(p.eta, p.d_omega, p.omega_max)
+    return SpectrumResult(float(r["superfluid_stiffness"][0]), float(r["dc_conductivity"][0]), r["omega_grid"],
+                          r["optical_conductivity"][0], r["dos_omega_grid"], r["dos"][0], r["dos_AN"][0], r["A_k_w0"][0])
+

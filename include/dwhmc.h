@@ -97,6 +97,18 @@ int dwhmc_total_energy(dwhmc_handle h, double* out);
 /* measure_observables(cache, p, state) src/Observables.jl:88-222 ; out: double[9 * B] */
 int dwhmc_measure_observables(dwhmc_handle h, double* out);
 
+/* measure_transport_and_spectra(cache, p) + build_current_operator!(cache, p)
+ * src/Observables.jl:314-526, :237-283, for every chain, from the current (E_n, U) and the
+ * fermi_factors left by the last compute_forces / measure_observables (as the reference, :321).
+ * eta = p.eta; omega_grid = collect(p.omega_min : p.d_omega : p.omega_max) (double[n_omega]) and
+ * dos_grid = collect(-p.omega_max : p.d_omega : p.omega_max) (double[n_dos]) are built by the caller.
+ * Outputs (SpectrumResult, :293-311): scalars double[2 * B] = (superfluid_stiffness, dc_conductivity)
+ * per chain; sigma double[n_omega * B]; dos, dos_AN double[n_dos * B]; A_k0 double[Lx * Ly * B]
+ * (column-major Lx x Ly per chain).  Any output may be NULL. */
+int dwhmc_measure_transport(dwhmc_handle h, double eta, const double* omega_grid, int n_omega,
+                            const double* dos_grid, int n_dos, double* scalars, double* sigma,
+                            double* dos, double* dos_AN, double* A_k0);
+
 /* cache getters (debug / parity): H_base as the reference stores it (upper
  * triangle, lower = 0; complex[n * n * B]), E_n (double[n * B]), U
  * (complex[n * n * B]), forces (complex[N * 2 * B]), fermi_factors (double[n * B]). */

@@ -332,6 +332,55 @@ def test_band_route_matches_dense_route(dw, monkeypatch):
     cb.close()
 
 
+@pytest.mark.parametrize("L,n_imp", [(8, 0.05), ((6, 10), 0.05), (8, 0.0)])
+def test_transport_and_spectra_match_oracle(dw, L, n_imp):
+    """measure_transport_and_spectra (src/Observables.jl:314-526) on the GPU against the oracle's restatement:
+    stiffness, dc conductivity, Re sigma(omega), DOS, antinodal DOS and A(k, 0); eta = 8/N, d_omega = 0.2 eta as in
+    scripts/batch_scan_T.jl:30-32.  Tolerance 1e-9 relative to the largest entry of each array."""
+    betas = [2.0, 20.0, 200.0]
+    cb, ps, sts, cs = make_batch(dw, L, betas, n_imp, 1500)
+    N = ps[0].N
+    eta = 8.0 / N
+    cb.compute_forces()                                   # leaves fermi_factors, as in the reference's sweep loop
+    r = cb.measure_transport_and_spectra(eta, 0.2 * eta, 4.0)
+    for b in range(len(betas)):
+        p = ps[b]
+        p.eta, p.d_omega, p.omega_max = eta, 0.2 * eta, 4.0
+        orc.compute_forces(cs[b], p, sts[b])
+        ref = orc.measure_transport_and_spectra(cs[b], p)
+        assert len(ref.omega_grid) == r["optical_conductivity"].shape[1]
+        assert np.allclose(ref.omega_grid, r["omega_grid"], rtol=0, atol=1e-14)
+        scale = max(abs(ref.superfluid_stiffness), 1e-3)
+        assert abs(r["superfluid_stiffness"][b] - ref.superfluid_stiffness) <= 1e-9 * max(scale, 1.0)
+        assert abs(r["dc_conductivity"][b] - ref.dc_conductivity) <= 1e-9 * max(abs(ref.dc_conductivity), 1e-6)
+        for key, arr in (("optical_conductivity", ref.optical_conductivity), ("dos", ref.dos), ("dos_AN", ref.dos_AN),
+                         ("A_k_w0", ref.A_k_w0)):
+            got = r[key][b]
+            assert got.shape == arr.shape, (key, got.shape, arr.shape)
+            assert np.max(np.abs(got - arr)) <= 1e-9 * max(np.max(np.abs(arr)), 1e-12), key
+    cb.close()
+
+
+def test_transport_single_chain_api(dw):
+    """Reads like the reference: measure_observables, then measure_transport_and_spectra(cache, p)."""
+    p = dw.ModelParameters(8, 8, 1.0, -0.35, -1.08, 1.0, 0.05, 20.0, 0.8, 1.0, eta=0.125, d_omega=0.025, omega_max=4.0)
+    po = orc.ModelParameters(8, 8, 1.0, -0.35, -1.08, 1.0, 0.05, 20.0, 0.8, 1.0, eta=0.125, d_omega=0.025, omega_max=4.0)
+    _, st, c = orc.make_chain(po, 1600)
+    state = dw.SimulationState(st.disorder_pot.copy(), st.Delta.copy(), np.zeros_like(st.Delta))
+    cache = dw.initialize_cache(p)
+    dw.init_static_H(cache, p, state); dw.update_H_BdG(cache, p, state); dw.diagonalize_H_BdG(cache, p)
+    dw.measure_observables(cache, p, state)
+    dw.build_current_operator(cache, p)
+    res = dw.measure_transport_and_spectra(cache, p)
+    orc.measure_observables(c, po, st)
+    ref = orc.measure_transport_and_spectra(c, po)
+    assert abs(res.superfluid_stiffness - ref.superfluid_stiffness) <= 1e-9
+    assert abs(res.dc_conductivity - ref.dc_conductivity) <= 1e-9 * max(abs(ref.dc_conductivity), 1e-6)
+    assert np.max(np.abs(res.dos - ref.dos)) <= 1e-9 * np.max(np.abs(ref.dos))
+    assert res.A_k_w0.shape == (8, 8)
+    cache.batch.close()
+
+
 def test_debug_stages(dw):
     import scipy.linalg as sl
     B, L = 2, 6
