@@ -315,7 +315,7 @@ int dw_transport(Handle* h, double eta, const double* omega_dev, int nw, const d
                  double* scal, double* sigma, double* dos, double* dosAN, double* ak, double* work, size_t work_count) {
   const int n = h->n, N = h->N, B = h->B;
   cplx* T = h->A;              // Jx U, then free
-  cplx* J = h->V;              // U^H Jx U (lower tiles)
+  cplx* J = h->U_prop;         // U^H Jx U (lower tiles); U_prop is free between trajectories (V must keep its zeros)
   double* J2 = h->Z0;          // |J|^2, full
   const int nchunk = (n + PCH - 1) / PCH;
   const int akchunk = (n + AKC - 1) / AKC;

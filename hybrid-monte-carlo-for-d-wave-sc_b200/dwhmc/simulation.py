@@ -6,10 +6,13 @@ The reference runs one chain per call and the scan scripts loop over temperature
   * adaptive thermalisation (:104-130): every 5 sweeps, acceptance < 0.60 -> Nt += 2,
     > 0.95 and Nt > 4 -> Nt -= 1, dt = calc_optimal_dt(beta, J, m, Nt) -- per chain;
   * measurement loop (:151-228): hmc_sweep!, measure_observables, one CSV row per sweep, flushed;
+  * every measure_transport_freq sweeps: measure_transport_and_spectra (:168-223), one transport.csv row
+    ("%d,%.6f,%.6f"), spectra averaged over bin_size measurements;
   * files per chain directory: simulation.log (append), observables.csv (truncate; 12 columns,
-    "%d,%d,%.5e" + 9 x ",%.6f"), transport.csv (header only: transport/spectra are not computed by
-    this library yet).
-Not written: spectra_bins.jld2 (needs the transport path)."""
+    "%d,%d,%.5e" + 9 x ",%.6f"), transport.csv, spectra_bins.npz.
+spectra_bins.npz stands in for the reference's spectra_bins.jld2 (JLD2 / HDF5 writers are not available to
+this host package): same keys -- "omega_grid", "dos_omega_grid", "params" (the ModelParameters scalars) and per bin
+"sweep_<i>/opt_cond", "/dos", "/dos_AN", "/A_k0", "/count"; INTEGRATION.md has the NPZ -> JLD2 snippet."""
 from __future__ import annotations
 
 import datetime
@@ -111,8 +114,37 @@ class _ChainFiles:
             f.close()
 
 
+class _SpectraBins:
+    """The binning of src/Simulation.jl:179-221 for one chain; `store` mirrors the JLD2 groups."""
+
+    def __init__(self, path: str, p: ModelParameters, omega_grid, dos_grid):
+        self.path, self.count, self.acc = path, 0, None
+        self.store = {"omega_grid": np.asarray(omega_grid), "dos_omega_grid": np.asarray(dos_grid),
+                      "params": np.array([p.Lx, p.Ly, p.t, p.tp, p.mu, p.W, p.n_imp, p.beta, p.J, p.mass, p.eta,
+                                          p.d_omega, p.omega_max])}
+        np.savez(self.path, **self.store)                       # jldsave(...; params, omega_grid) at :89
+
+    def add(self, sweep: int, bin_size: int, opt_cond, dos, dos_AN, ak0):
+        new = [np.array(a, dtype=np.float64) for a in (opt_cond, dos, dos_AN, ak0)]
+        if self.count == 0:
+            self.acc, self.count = new, 1
+        else:
+            for a, b in zip(self.acc, new):
+                a += b
+            self.count += 1
+        if self.count >= bin_size:
+            for a in self.acc:
+                a /= self.count
+            for key, a in zip(("opt_cond", "dos", "dos_AN", "A_k0"), self.acc):
+                self.store[f"sweep_{sweep}/{key}"] = a
+            self.store[f"sweep_{sweep}/count"] = np.array(self.count)
+            np.savez(self.path, **self.store)
+            self.count = 0
+
+
 def run_simulation_batch(params: Sequence[ModelParameters], out_dirs: Sequence[str], *, n_therm: int = 100,
-                         n_measure: int = 500, Nt_therm_init: int = 10, Nt_measure: int = 5, device: int = 0,
+                         n_measure: int = 500, Nt_therm_init: int = 10, Nt_measure: int = 5,
+                         measure_transport_freq: int = 0, bin_size: int = 5, device: int = 0,
                          seeds: Sequence[int] | None = None, rng_mode: str = "device", verbose: bool = False):
     """run_simulation for len(params) chains sharing one lattice, in lock-step on one GPU.
     rng_mode "device": Philox momenta/uniforms on the GPU (throughput); "host": NumPy generators per
@@ -129,7 +161,8 @@ def run_simulation_batch(params: Sequence[ModelParameters], out_dirs: Sequence[s
     for f, p in zip(files, params):
         f.tee("Starting Simulation...")
         f.tee(f"System: {p.Lx}x{p.Ly}, β={p.beta}, n_imp={p.n_imp}, J={p.J}")
-        f.tee(f"Config: Therm={n_therm}, Sweep={n_measure}, TransFreq=off, BinSize=off (B200 batch of {B} chains)")
+        f.tee(f"Config: Therm={n_therm}, Sweep={n_measure}, TransFreq={measure_transport_freq}, BinSize={bin_size}"
+              f" (B200 batch of {B} chains)")
         f.tee("Initializing State...")
     states = [initialize_state(p, r) for p, r in zip(params, rngs)]
     cb = ChainBatch(B, p0.Lx, p0.Ly, device=device, nn_table=p0.nn_table, nnn_table=p0.nnn_table)
@@ -188,6 +221,10 @@ def run_simulation_batch(params: Sequence[ModelParameters], out_dirs: Sequence[s
             f.tee(f"Settings: Nt={Nt_measure}, dt={round(dtm[b], 5)}")
         table = np.zeros((n_measure, B, 12))
         acc_total = np.zeros(B, dtype=int)
+        transport_rows, bins = [], None
+        if measure_transport_freq > 0:
+            assert all((p.eta, p.d_omega, p.omega_max) == (p0.eta, p0.d_omega, p0.omega_max) for p in params), \
+                "chains of one batch share the frequency grids"
         for i in range(1, n_measure + 1):
             acc, dH = sweep(Ntm, dtm)
             acc_total += acc
@@ -196,12 +233,23 @@ def run_simulation_batch(params: Sequence[ModelParameters], out_dirs: Sequence[s
                 files[b].obs.write(obs_csv_line(i, acc[b], dH[b], obs[b]))
                 files[b].obs.flush()
                 table[i - 1, b] = (i, acc[b], dH[b], *obs[b])
+            if measure_transport_freq > 0 and i % measure_transport_freq == 0:
+                sp = cb.measure_transport_and_spectra(p0.eta, p0.d_omega, p0.omega_max)
+                if bins is None:
+                    bins = [_SpectraBins(os.path.join(d, "spectra_bins.npz"), p, sp["omega_grid"], sp["dos_omega_grid"])
+                            for d, p in zip(out_dirs, params)]
+                transport_rows.append((i, sp["superfluid_stiffness"].copy(), sp["dc_conductivity"].copy()))
+                for b in range(B):
+                    files[b].trans.write("%d,%.6f,%.6f\n" % (i, sp["superfluid_stiffness"][b], sp["dc_conductivity"][b]))
+                    files[b].trans.flush()
+                    bins[b].add(i, bin_size, sp["optical_conductivity"][b], sp["dos"][b], sp["dos_AN"][b], sp["A_k_w0"][b])
+            for b in range(B):
                 if i % 10 == 0:
                     files[b].tee("Meas %d/%d. Acc=%.2f. E=%.4f" % (i, n_measure, acc_total[b] / i, obs[b, 0]))
         for f in files:
             f.tee("Measurement Done.")
         return {"table": table, "Nt_therm_final": Nt_final, "acceptance": acc_total / max(n_measure, 1),
-                "field": cb.get_field()}
+                "field": cb.get_field(), "transport": transport_rows}
     finally:
         cb.close()
         for f in files:
@@ -211,15 +259,15 @@ def run_simulation_batch(params: Sequence[ModelParameters], out_dirs: Sequence[s
 def run_simulation(p: ModelParameters, out_dir: str, *, n_therm: int = 100, n_measure: int = 500,
                    Nt_therm_init: int = 10, Nt_measure: int = 5, measure_transport_freq: int = 1, bin_size: int = 5,
                    verbose: bool = True, seed: int = 0, device: int = 0, rng_mode: str = "device"):
-    """Single-chain form with the reference's keyword names (src/Simulation.jl:34-41);
-    measure_transport_freq and bin_size are accepted and ignored (no transport path yet)."""
+    """Single-chain form with the reference's keyword names and defaults (src/Simulation.jl:34-41)."""
     return run_simulation_batch([p], [out_dir], n_therm=n_therm, n_measure=n_measure, Nt_therm_init=Nt_therm_init,
-                                Nt_measure=Nt_measure, device=device, seeds=[seed], rng_mode=rng_mode, verbose=verbose)
+                                Nt_measure=Nt_measure, measure_transport_freq=measure_transport_freq, bin_size=bin_size,
+                                device=device, seeds=[seed], rng_mode=rng_mode, verbose=verbose)
 
 
 def batch_scan_T(base_dir: str, Ts: Sequence[float], n_seeds: int = 1, *, Lx: int = 24, Ly: int = 24, t=1.0, tp=-0.35,
                  mu=-1.08, W=1.0, n_imp=0.05, J=0.8, mass=1.0, n_therm=20, n_measure=100, Nt_therm=20, Nt_measure=6,
-                 device: int = 0, chain_ids: Sequence[int] | None = None, **kw):
+                 measure_freq: int = 1, bin_size: int = 10, device: int = 0, chain_ids: Sequence[int] | None = None, **kw):
     """scripts/batch_scan_T.jl as one batch: chain c = (temperature c // n_seeds, seed c % n_seeds);
     directory T_<round(T, sigdigits=3)> (plus /seed_<k> when n_seeds > 1).  `chain_ids` restricts the
     call to this rank's shard (dwhmc.parallel.shard_chains)."""
@@ -234,4 +282,5 @@ def batch_scan_T(base_dir: str, Ts: Sequence[float], n_seeds: int = 1, *, Lx: in
         dirs.append(d if n_seeds == 1 else os.path.join(d, f"seed_{k}"))
         seeds.append(1_000_000 * 3 + 1000 * ip + k)
     return run_simulation_batch(ps, dirs, n_therm=n_therm, n_measure=n_measure, Nt_therm_init=Nt_therm,
-                                Nt_measure=Nt_measure, device=device, seeds=seeds, **kw)
+                                Nt_measure=Nt_measure, measure_transport_freq=measure_freq, bin_size=bin_size,
+                                device=device, seeds=seeds, **kw)

@@ -485,12 +485,19 @@ def test_batched_run_driver_matches_oracle_run(dw, tmp_path):
     betas, seeds = [5.0, 40.0], [11, 12]
     ps = [dw.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.1, b, PHYS["J"], PHYS["mass"]) for b in betas]
     dirs = [str(tmp_path / sim.scan_dir_T(1.0 / b)) for b in betas]
+    for p in ps:
+        p.eta, p.d_omega, p.omega_max = 0.5, 0.1, 4.0
     out = sim.run_simulation_batch(ps, dirs, n_therm=n_therm, n_measure=n_meas, Nt_therm_init=Nt0, Nt_measure=Ntm,
-                                   seeds=seeds, rng_mode="host")
+                                   measure_transport_freq=2, bin_size=2, seeds=seeds, rng_mode="host")
     for c, (beta, seed) in enumerate(zip(betas, seeds)):
-        p = orc.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.1, beta, PHYS["J"], PHYS["mass"])
+        p = orc.ModelParameters(L, L, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], 0.1, beta, PHYS["J"], PHYS["mass"],
+                                eta=0.5, d_omega=0.1, omega_max=4.0)
         rng, st, ca = orc.make_chain(p, seed)
         Nt, recent = Nt0, 0
+        trans_rows = open(os.path.join(dirs[c], "transport.csv")).read().splitlines()
+        assert trans_rows[0] == sim.TRANS_HEADER and len(trans_rows) == 1 + n_meas // 2
+        bins = np.load(os.path.join(dirs[c], "spectra_bins.npz"))
+        acc_spec, n_in_bin = None, 0
         dt = orc.calc_optimal_dt(p.beta, p.J, p.mass, Nt)
         for i in range(1, n_therm + 1):
             acc, _ = orc.hmc_sweep(ca, p, st, Nt=Nt, dt=dt, rng=rng)
@@ -510,5 +517,20 @@ def test_batched_run_driver_matches_oracle_run(dw, tmp_path):
             assert abs(row[2] - dH) <= 1e-9 * max(abs(Ho), 1.0)
             assert np.allclose(row[3:], obs, rtol=1e-7, atol=1e-9)
             assert rows[i] == sim.obs_csv_line(i, acc, row[2], row[3:]).rstrip("\n")
-        assert open(os.path.join(dirs[c], "transport.csv")).read().strip() == sim.TRANS_HEADER
+            if i % 2 == 0:                                   # measure_transport_freq = 2, bin_size = 2
+                sp = orc.measure_transport_and_spectra(ca, p)
+                k = i // 2
+                it, stiff, dc = trans_rows[k].split(",")
+                assert int(it) == i and abs(float(stiff) - sp.superfluid_stiffness) <= 2e-6
+                assert abs(float(dc) - sp.dc_conductivity) <= 2e-6 * max(1.0, abs(sp.dc_conductivity))
+                cur = [sp.optical_conductivity, sp.dos, sp.dos_AN, sp.A_k_w0]
+                acc_spec = [a.copy() for a in cur] if n_in_bin == 0 else [a + b for a, b in zip(acc_spec, cur)]
+                n_in_bin += 1
+                if n_in_bin >= 2:
+                    for key, a in zip(("opt_cond", "dos", "dos_AN", "A_k0"), acc_spec):
+                        got = bins[f"sweep_{i}/{key}"]
+                        assert np.max(np.abs(got - a / n_in_bin)) <= 1e-8 * max(np.max(np.abs(a)), 1e-12), key
+                    assert int(bins[f"sweep_{i}/count"]) == 2
+                    n_in_bin = 0
+        assert np.allclose(bins["omega_grid"], orc.julia_range(p.eta, p.d_omega, p.omega_max))
         assert "Measurement Done." in open(os.path.join(dirs[c], "simulation.log")).read()
