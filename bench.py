@@ -178,7 +178,7 @@ def run_reference(args):
            "note": "Julia is not installed, so the reference cannot run; this arm times oracle/dwhmc_oracle.py, the "
                    "NumPy/SciPy restatement that calls the same LAPACK zheevr; each step = one bounded sample (see cpu_baseline.sample)",
            "wall_s": el}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args):
@@ -330,10 +330,33 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": desc},
             "gathered_table_shape": list(table.shape),
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     cb.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+class _CleanStdout:
+    """Everything libraries print to fd 1 while the bench runs (e.g. NCCL's version banner) goes to
+    stderr; only the JSON line reaches stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_JSON_LINES = []
+
+
+def emit(obj):
+    _JSON_LINES.append(json.dumps(obj))
 
 
 def main():
@@ -350,10 +373,13 @@ def main():
     if args.cpu_worker:
         print(_oracle_trajectories(args.L, args.nt, 1), flush=True)
         return
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _CleanStdout():
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    for ln in _JSON_LINES:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":

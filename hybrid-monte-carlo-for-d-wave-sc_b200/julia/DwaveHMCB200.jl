@@ -33,7 +33,7 @@ function check(h::Ptr{Cvoid}, rc::Cint)
 end
 
 """One chain on one GPU.  Holds the device handle; `E_n`, `U`, `forces`, `fermi_factors` are host
-mirrors filled on demand by `fetch_eigensystem!` (measure_transport_and_spectra needs U and E_n)."""
+mirrors filled on demand by `fetch_eigensystem!`."""
 mutable struct B200Cache
     h::Ptr{Cvoid}
     N::Int
@@ -135,7 +135,22 @@ function measure_observables(c::B200Cache, p, state)
     return out        # wrap as DwaveHMC.ObservablesResult(out...) at the call site
 end
 
-"""Copy E_n and U back to the host mirrors (for measure_transport_and_spectra, which stays Julia)."""
+# measure_transport_and_spectra + build_current_operator!  (src/Observables.jl:314-526, :237-283).
+# Returns the fields of SpectrumResult (:293-311) in order; wrap as DwaveHMC.SpectrumResult(r...) at the call site.
+build_current_operator!(c::B200Cache, p) = (sync_params!(c, p); nothing)   # the operator lives in the kernels
+function measure_transport_and_spectra(c::B200Cache, p)
+    sync_params!(c, p)
+    ω = collect(p.ω_min:p.Δω:p.ω_max); ωd = collect(-p.ω_max:p.Δω:p.ω_max)
+    scal = zeros(2); σ = zeros(length(ω)); dos = zeros(length(ωd)); dosAN = zeros(length(ωd))
+    Ak0 = zeros(p.Lx, p.Ly)
+    check(c.h, ccall((:dwhmc_measure_transport, LIB), Cint,
+                     (Ptr{Cvoid}, Cdouble, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64},
+                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     c.h, p.η, ω, length(ω), ωd, length(ωd), scal, σ, dos, dosAN, Ak0))
+    return (scal[1], scal[2], ω, σ, ωd, dos, dosAN, Ak0)
+end
+
+"""Copy E_n and U back to the host mirrors (debugging; the transport path no longer needs them on the host)."""
 function fetch_eigensystem!(c::B200Cache)
     check(c.h, ccall((:dwhmc_get_eigenvalues, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.h, c.E_n))
     check(c.h, ccall((:dwhmc_get_eigenvectors, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), c.h, c.U))
