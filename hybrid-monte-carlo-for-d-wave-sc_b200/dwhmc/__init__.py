@@ -6,4 +6,4 @@ from .batch import ChainBatch, OBS_NAMES, calc_optimal_dt, julia_range, neighbou
 from .reference_api import (ComputeCache, ModelParameters, ObservablesResult, SimulationState, SpectrumResult,  # noqa: F401
                             build_current_operator, measure_transport_and_spectra, compute_forces, compute_total_energy, diagonalize_H_BdG, hmc_sweep, init_static_H,
                             initialize_cache, initialize_state, measure_observables, refresh_momentum, update_H_BdG)
-from .simulation import batch_scan_T, run_simulation, run_simulation_batch  # noqa: E402,F401
+from .simulation import batch_scan_T, batch_scan_beta, run_simulation, run_simulation_batch, scan_Nt_efficiency  # noqa: E402,F401

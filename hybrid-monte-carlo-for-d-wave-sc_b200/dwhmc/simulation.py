@@ -284,3 +284,48 @@ def batch_scan_T(base_dir: str, Ts: Sequence[float], n_seeds: int = 1, *, Lx: in
     return run_simulation_batch(ps, dirs, n_therm=n_therm, n_measure=n_measure, Nt_therm_init=Nt_therm,
                                 Nt_measure=Nt_measure, measure_transport_freq=measure_freq, bin_size=bin_size,
                                 device=device, seeds=seeds, **kw)
+
+
+def batch_scan_beta(base_dir: str, betas: Sequence[float], *, Lx: int = 12, Ly: int = 12, t=1.0, tp=-0.35, mu=-1.08,
+                    W=1.0, n_imp=0.0, J=0.8, mass=1.0, n_therm=20, n_measure=100, Nt_therm=20, Nt_measure=6,
+                    measure_freq: int = 1, bin_size: int = 10, device: int = 0,
+                    chain_ids: Sequence[int] | None = None, **kw):
+    """scripts/batch_scan_beta.jl:52-71 as one batch: one chain per beta, directory beta_<round(beta, digits=3)>;
+    eta = 8/N, d_omega = 0.2 eta, omega_max = 4 (:15-17)."""
+    ids = list(range(len(betas))) if chain_ids is None else [int(c) for c in chain_ids]
+    ps, dirs, seeds = [], [], []
+    for c in ids:
+        beta = float(betas[c])
+        ps.append(ModelParameters(Lx, Ly, t, tp, mu, W, n_imp, beta, J, mass, eta=8.0 / (Lx * Ly),
+                                  d_omega=0.2 * 8.0 / (Lx * Ly), omega_max=4.0))
+        dirs.append(os.path.join(base_dir, scan_dir_beta(beta)))
+        seeds.append(4_000_000 + 1000 * c)
+    return run_simulation_batch(ps, dirs, n_therm=n_therm, n_measure=n_measure, Nt_therm_init=Nt_therm,
+                                Nt_measure=Nt_measure, measure_transport_freq=measure_freq, bin_size=bin_size,
+                                device=device, seeds=seeds, **kw)
+
+
+def scan_Nt_efficiency(Nt_list: Sequence[int] = (2, 3, 4, 5, 6, 8, 10, 12, 15, 20, 30), *, Lx: int = 10, Ly: int = 10,
+                       t=1.0, tp=-0.35, mu=-1.08, W=3.0, n_imp=0.078, beta=20.0, J=0.8, mass=1.0, n_warmup: int = 100,
+                       n_measure: int = 100, seed: int = 0, device: int = 0):
+    """scripts/test_scan_Nt_efficiency.jl:19-62: acceptance and Acc/Nt against the number of leapfrog steps at a
+    fixed trajectory length L = 2 pi sqrt(m J / beta) (dt = L / Nt).  The reference runs the Nt values one after
+    another from fresh states; here they are the chains of one batch (same disorder / Delta0 seed for all).
+    Returns (Nt, dt, acceptance, efficiency) arrays."""
+    Nts = np.asarray(list(Nt_list), dtype=np.int32)
+    B = len(Nts)
+    p = ModelParameters(Lx, Ly, t, tp, mu, W, n_imp, beta, J, mass)
+    L_target = 2.0 * math.pi * math.sqrt(mass * J / beta)          # T_period / 2, T_period = 4 pi sqrt(m J / beta)
+    dt = L_target / Nts
+    st = initialize_state(p, np.random.Generator(np.random.PCG64(seed)))
+    with ChainBatch(B, Lx, Ly, device=device, nn_table=p.nn_table, nnn_table=p.nnn_table) as cb:
+        cb.set_params(t, tp, mu, beta, J, mass)
+        cb.set_disorder(np.tile(st.disorder_pot, (B, 1)))
+        cb.set_field(np.tile(st.Delta.T[None], (B, 1, 1)))
+        cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+        cb.seed(seed * 31 + 5)
+        cb.run_sweeps(n_warmup, Nts, dt)
+        nacc, _, _ = cb.run_sweeps(n_measure, Nts, dt)
+    rate = nacc / max(n_measure, 1)
+    return Nts, dt, rate, rate / Nts
+

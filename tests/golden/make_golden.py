@@ -57,11 +57,41 @@ def run_case(L, n_imp, beta, Nt, n_sweeps, seed):
     return out
 
 
+TRANSPORT_CASES = {
+    # name: (L, n_imp, beta, seed); eta = 8/N, d_omega = 0.2 eta, omega_max = 4 (scripts/batch_scan_T.jl:30-32)
+    "transport_L8_dis_b20": (8, 0.05, 20.0, 3001),
+    "transport_L6x10_dis_b200": ((6, 10), 0.05, 200.0, 3002),
+}
+
+
+def run_transport_case(L, n_imp, beta, seed):
+    """measure_transport_and_spectra (src/Observables.jl:314-526) on the seeded initial state, after
+    measure_observables (which leaves fermi_factors, as in the reference's sweep loop)."""
+    Lx, Ly = (L, L) if isinstance(L, int) else L
+    eta = 8.0 / (Lx * Ly)
+    p = orc.ModelParameters(Lx, Ly, PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], n_imp, beta, PHYS["J"],
+                            PHYS["mass"], eta=eta, d_omega=0.2 * eta, omega_max=4.0)
+    _, st, c = orc.make_chain(p, seed)
+    orc.measure_observables(c, p, st)
+    r = orc.measure_transport_and_spectra(c, p)
+    return dict(Lx=Lx, Ly=Ly, n_imp=n_imp, beta=beta, seed=seed, eta=eta, d_omega=0.2 * eta, omega_max=4.0,
+                disorder=st.disorder_pot.copy(), Delta0=st.Delta.copy(), stiffness=r.superfluid_stiffness,
+                dc=r.dc_conductivity, omega_grid=r.omega_grid, sigma=r.optical_conductivity,
+                dos_grid=r.dos_omega_grid, dos=r.dos, dos_AN=r.dos_AN, A_k0=r.A_k_w0)
+
+
 def main():
+    only_transport = "--transport-only" in sys.argv
     for name, args in CASES.items():
+        if only_transport:
+            break
         out = run_case(*args)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "dH", out["dH"], "acc", out["accepted"])
+    for name, args in TRANSPORT_CASES.items():
+        out = run_transport_case(*args)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "stiffness", out["stiffness"], "dc", out["dc"])
 
 
 if __name__ == "__main__":

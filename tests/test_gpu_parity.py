@@ -15,7 +15,9 @@ import dwhmc_oracle as orc  # noqa: E402  (checker only)
 
 RTOL = 1e-10
 PHYS = dict(t=1.0, tp=-0.35, mu=-1.08, W=1.0, J=0.8, mass=1.0)
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL_GOLDEN if not os.path.basename(p).startswith("transport_")]
+TRANSPORT_GOLDEN = [p for p in _ALL_GOLDEN if os.path.basename(p).startswith("transport_")]
 
 
 @pytest.fixture(scope="module")
@@ -361,6 +363,26 @@ def test_transport_and_spectra_match_oracle(dw, L, n_imp):
     cb.close()
 
 
+@pytest.mark.parametrize("path", TRANSPORT_GOLDEN, ids=[os.path.basename(p)[:-4] for p in TRANSPORT_GOLDEN])
+def test_transport_golden_vectors(dw, path):
+    """The committed transport / spectra vectors (tests/golden/make_golden.py) through the single-chain API."""
+    g = np.load(path)
+    p = dw.ModelParameters(int(g["Lx"]), int(g["Ly"]), PHYS["t"], PHYS["tp"], PHYS["mu"], PHYS["W"], float(g["n_imp"]),
+                           float(g["beta"]), PHYS["J"], PHYS["mass"], eta=float(g["eta"]), d_omega=float(g["d_omega"]),
+                           omega_max=float(g["omega_max"]))
+    state = dw.SimulationState(g["disorder"].copy(), g["Delta0"].copy(), np.zeros_like(g["Delta0"]))
+    cache = dw.initialize_cache(p)
+    dw.init_static_H(cache, p, state); dw.update_H_BdG(cache, p, state); dw.diagonalize_H_BdG(cache, p)
+    dw.measure_observables(cache, p, state)
+    r = dw.measure_transport_and_spectra(cache, p)
+    assert abs(r.superfluid_stiffness - float(g["stiffness"])) <= 1e-9
+    assert abs(r.dc_conductivity - float(g["dc"])) <= 1e-9 * max(1.0, abs(float(g["dc"])))
+    assert np.allclose(r.omega_grid, g["omega_grid"], rtol=0, atol=1e-14)
+    for got, key in ((r.optical_conductivity, "sigma"), (r.dos, "dos"), (r.dos_AN, "dos_AN"), (r.A_k_w0, "A_k0")):
+        assert np.max(np.abs(got - g[key])) <= 1e-9 * max(np.max(np.abs(g[key])), 1e-12), key
+    cache.batch.close()
+
+
 def test_transport_single_chain_api(dw):
     """Reads like the reference: measure_observables, then measure_transport_and_spectra(cache, p)."""
     p = dw.ModelParameters(8, 8, 1.0, -0.35, -1.08, 1.0, 0.05, 20.0, 0.8, 1.0, eta=0.125, d_omega=0.025, omega_max=4.0)
@@ -534,3 +556,27 @@ def test_batched_run_driver_matches_oracle_run(dw, tmp_path):
                     n_in_bin = 0
         assert np.allclose(bins["omega_grid"], orc.julia_range(p.eta, p.d_omega, p.omega_max))
         assert "Measurement Done." in open(os.path.join(dirs[c], "simulation.log")).read()
+
+
+def test_scan_drivers_config4(dw, tmp_path):
+    """BASELINE config 4 shapes at a small size: the beta scan (scripts/batch_scan_beta.jl) as one batch with
+    transport every sweep, and the Nt-efficiency study (scripts/test_scan_Nt_efficiency.jl): acceptance rises with
+    the number of leapfrog steps at fixed trajectory length and a 30-step trajectory is accepted almost always."""
+    from dwhmc import simulation as sim
+    betas = 10.0 ** np.linspace(-2, 5, 4)
+    out = sim.batch_scan_beta(str(tmp_path), betas, Lx=6, Ly=6, n_therm=5, n_measure=4, Nt_therm=6, Nt_measure=6,
+                              bin_size=2)
+    assert out["table"].shape == (4, 4, 12) and len(out["transport"]) == 4
+    for b in betas:
+        d = tmp_path / sim.scan_dir_beta(b)
+        assert len(open(d / "observables.csv").read().splitlines()) == 5
+        assert len(open(d / "transport.csv").read().splitlines()) == 5
+        z = np.load(d / "spectra_bins.npz")
+        assert "sweep_2/dos" in z and "sweep_4/opt_cond" in z and int(z["sweep_4/count"]) == 2
+        assert np.all(np.isfinite(z["sweep_4/A_k0"]))
+    assert os.path.basename(str(tmp_path / sim.scan_dir_beta(0.01))) == "beta_0.01"
+    Nts, dt, rate, eff = sim.scan_Nt_efficiency((2, 6, 30), Lx=6, Ly=6, n_warmup=10, n_measure=40, seed=3)
+    assert np.allclose(Nts * dt, 2 * np.pi * np.sqrt(0.8 / 20.0))
+    assert rate[2] >= 0.9 and rate[2] >= rate[0] - 0.05
+    assert np.allclose(eff, rate / Nts)
+

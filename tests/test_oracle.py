@@ -37,7 +37,40 @@ def test_logexp_functions():
     assert np.allclose(orc.logistic(x[2:8]), 1 / (1 + np.exp(-x[2:8])), rtol=1e-15)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))))
+TRANSPORT_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "transport_*.npz")))
+
+
+@pytest.mark.parametrize("path", TRANSPORT_GOLDEN, ids=[os.path.basename(p)[:-4] for p in TRANSPORT_GOLDEN])
+def test_transport_golden_reproduced_and_sum_rules(path):
+    """The transport / spectra restatement reproduces its committed vectors, and obeys the checks the physics
+    offers: the DOS integrates to the particle weight (Lorentzian tails aside), A(k, 0) sums to the zero-energy
+    particle weight (Parseval), sigma(omega) >= 0 and the antinodal DOS is non-negative."""
+    g = np.load(path)
+    Lx, Ly = int(g["Lx"]), int(g["Ly"])
+    p = orc.ModelParameters(Lx, Ly, 1.0, -0.35, -1.08, 1.0, float(g["n_imp"]), float(g["beta"]), 0.8, 1.0,
+                            eta=float(g["eta"]), d_omega=float(g["d_omega"]), omega_max=float(g["omega_max"]))
+    st = orc.SimulationState(g["disorder"].copy(), g["Delta0"].copy(), np.zeros_like(g["Delta0"]))
+    c = orc.initialize_cache(p)
+    orc.init_static_H(c, p, st); orc.update_H_BdG(c, p, st); orc.diagonalize_H_BdG(c, p)
+    orc.measure_observables(c, p, st)
+    r = orc.measure_transport_and_spectra(c, p)
+    assert abs(r.superfluid_stiffness - float(g["stiffness"])) <= 1e-10
+    assert abs(r.dc_conductivity - float(g["dc"])) <= 1e-10 * max(1.0, abs(float(g["dc"])))
+    for got, key in ((r.optical_conductivity, "sigma"), (r.dos, "dos"), (r.dos_AN, "dos_AN"), (r.A_k_w0, "A_k0")):
+        assert np.max(np.abs(got - g[key])) <= 1e-10 * max(np.max(np.abs(g[key])), 1e-12), key
+    N = p.N
+    w_n = np.sum(np.abs(c.U[:N]) ** 2, axis=0)
+    inside = np.abs(c.E_n) < p.omega_max - 20 * p.eta
+    integral = np.sum(r.dos) * p.d_omega
+    assert abs(integral - np.sum(w_n) / N) <= 0.05 + np.sum(w_n[~inside]) / N
+    w0 = orc.lorentzian(-c.E_n, p.eta)
+    sel = w0 > 1e-6
+    assert abs(np.sum(r.A_k_w0) - np.sum(w_n[sel] * w0[sel])) <= 1e-9 * max(np.sum(r.A_k_w0), 1.0)
+    assert np.all(r.optical_conductivity >= -1e-12) and np.all(r.dos_AN >= 0)
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                                        if not os.path.basename(p).startswith("transport_")))
 def test_golden_reproduced(path):
     g = np.load(path)
     p = params((int(g["Lx"]), int(g["Ly"])), float(g["n_imp"]), float(g["beta"]))
