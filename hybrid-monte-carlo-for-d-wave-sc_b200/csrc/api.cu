@@ -159,7 +159,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   AL(h->Z0, nnB); AL(h->Z1, nnB); AL(h->S, nnB);
   AL(h->perm, nB); AL(h->ord, nB);
   AL(h->zvec, nB); AL(h->dl, nB); AL(h->wv, nB); AL(h->dnew, nB); AL(h->zhat, nB); AL(h->stau, nB);
-  AL(h->ndl, nB); AL(h->dfl, nB); AL(h->sorg, nB);
+  AL(h->ndl, nB); AL(h->dfl, nB); AL(h->sorg, nB); AL(h->ndc, nB); AL(h->kcls, nB + 2);
   {
     dwcore::DeflRot* r = nullptr;
     if ((rc = dalloc(h, r, nB)) != DWHMC_OK) return fail(rc);
@@ -261,6 +261,11 @@ int dwhmc_set_disorder(dwhmc_handle hh, const double* w) {
   if (!w) BADARG("dwhmc_set_disorder: NULL");
   return h2d(h, h->w, w, sizeof(double) * (size_t)h->N * h->B);
 }
+int dwhmc_get_disorder(dwhmc_handle hh, double* w) {
+  H_ENTER(hh);
+  if (!w) BADARG("dwhmc_get_disorder: NULL");
+  return d2h(h, w, h->w, sizeof(double) * (size_t)h->N * h->B);
+}
 int dwhmc_set_field(dwhmc_handle hh, const double* delta) {
   H_ENTER(hh);
   if (!delta) BADARG("dwhmc_set_field: NULL");
@@ -281,6 +286,19 @@ int dwhmc_get_momentum(dwhmc_handle hh, double* pi) {
   if (!pi) BADARG("dwhmc_get_momentum: NULL");
   return d2h(h, pi, h->pi, sizeof(cplx) * (size_t)h->n * h->B);
 }
+int dwhmc_init_state(dwhmc_handle hh, const double* W, const double* n_imp) {
+  H_ENTER(hh);
+  if (!W || !n_imp) BADARG("dwhmc_init_state: NULL");
+  for (int b = 0; b < h->B; ++b)
+    if (!(n_imp[b] >= 0.0 && n_imp[b] <= 1.0)) BADARG("dwhmc_init_state: n_imp must lie in [0, 1]");
+  // unif_dev / dH_dev double as the parameter staging area ([B] doubles each)
+  DW_TRY(h2d(h, h->unif_dev, W, sizeof(double) * h->B));
+  DW_TRY(h2d(h, h->dH_dev, n_imp, sizeof(double) * h->B));
+  DW_TRY(dw_init_state(h, h->unif_dev, h->dH_dev));
+  DW_CUDA(h, cudaStreamSynchronize(h->stream));
+  return DWHMC_OK;
+}
+
 int dwhmc_seed(dwhmc_handle hh, uint64_t seed) {
   H_ENTER(hh);
   h->seed = seed;

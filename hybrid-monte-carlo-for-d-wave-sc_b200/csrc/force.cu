@@ -201,6 +201,39 @@ __global__ void uniform_kernel(double* __restrict__ u, int B, unsigned long long
   u[b] = (double)x * 1.1102230246251565e-16;   // [0, 1)
 }
 
+// initialize_state (src/Types.jl:118-134) on the device: round(N n_imp) distinct uniformly random sites get the
+// potential W (partial Fisher-Yates, one thread per chain: N is at most a few thousand), Delta0 has
+// Re, Im ~ U[-0.05, 0.05) independently on every bond; pi = 0.
+__global__ void __launch_bounds__(256) init_state_kernel(double* __restrict__ w, cplx* __restrict__ delta, cplx* __restrict__ pi,
+                                                         const double* __restrict__ Wv, const double* __restrict__ nimp,
+                                                         int N, int B, unsigned long long seed, unsigned long long counter) {
+  const int b = blockIdx.x;
+  extern __shared__ int sperm[];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { sperm[i] = i; w[(size_t)b * N + i] = 0.0; }
+  for (int q = threadIdx.x; q < 2 * N; q += blockDim.x) {
+    uint32_t r[4];
+    philox((uint32_t)q, (uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32) ^ 0x3u, (uint32_t)seed,
+           (uint32_t)(seed >> 32), r);
+    const double u1 = (double)((((unsigned long long)r[0] << 32) | r[1]) >> 11) * 1.1102230246251565e-16;
+    const double u2 = (double)((((unsigned long long)r[2] << 32) | r[3]) >> 11) * 1.1102230246251565e-16;
+    delta[(size_t)b * 2 * N + q] = make_double2((u1 - 0.5) * 0.1, (u2 - 0.5) * 0.1);
+    pi[(size_t)b * 2 * N + q] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nimp_sites = (int)rint((double)N * nimp[b]);          // Julia round: ties to even
+    for (int k = 0; k < nimp_sites && k < N; ++k) {
+      uint32_t r[4];
+      philox((uint32_t)k, (uint32_t)b, (uint32_t)counter, (uint32_t)(counter >> 32) ^ 0x4u, (uint32_t)seed,
+             (uint32_t)(seed >> 32), r);
+      const unsigned long long x = (((unsigned long long)r[0] << 32) | r[1]);
+      const int j = k + (int)(x % (unsigned long long)(N - k));
+      const int t = sperm[k]; sperm[k] = sperm[j]; sperm[j] = t;
+      w[(size_t)b * N + sperm[k]] = Wv[b];
+    }
+  }
+}
+
 __global__ void dH_kernel(const double* __restrict__ Hold, const double* __restrict__ Hnew, double* __restrict__ dH, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) dH[b] = Hnew[b] - Hold[b];
@@ -374,6 +407,13 @@ int dw_observables(Handle* h, double* out_dev) {
 int dw_refresh_momentum(Handle* h) {
   dim3 grid((2 * h->N + 255) / 256, h->B);
   momentum_kernel<<<grid, 256, 0, h->stream>>>(h->pi, h->par, h->N, h->B, h->seed, h->rng_counter++);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
+int dw_init_state(Handle* h, const double* W_dev, const double* nimp_dev) {
+  init_state_kernel<<<h->B, 256, sizeof(int) * h->N, h->stream>>>(h->w, h->delta, h->pi, W_dev, nimp_dev, h->N, h->B, h->seed,
+                                                                   h->rng_counter++);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }

@@ -113,6 +113,7 @@ struct Handle {
   int* ord = nullptr;           // [n*B]
   double *zvec = nullptr, *dl = nullptr, *wv = nullptr, *dnew = nullptr, *zhat = nullptr, *stau = nullptr;  // [n*B]
   int *ndl = nullptr, *dfl = nullptr, *sorg = nullptr;   // [n*B]
+  int *ndc = nullptr, *kcls = nullptr;                   // [n*B] class-ordered non-deflated columns, class counts
   void* rots = nullptr;         // [n*B] DeflRot
   int* kcnt = nullptr;          // [n*B] indexed by b*n + merge offset
   int* nrot = nullptr;          // [n*B]
@@ -227,6 +228,7 @@ size_t dw_transport_work_count(const Handle* h, int nw);
 int dw_forces(Handle* h, const double* E, const cplx* U, int mode, int step);
 int dw_total_energy(Handle* h, const double* E, double* out_dev);   // out_dev [B]
 int dw_observables(Handle* h, double* out_dev);                     // out_dev [9*B], uses E_cur/U_cur
+int dw_init_state(Handle* h, const double* W_dev, const double* nimp_dev);   // initialize_state on the device
 int dw_refresh_momentum(Handle* h);                                 // Philox N(0, m)
 int dw_uniforms(Handle* h);                                         // Philox U[0,1) -> h->unif_dev
 int dw_begin_trajectory(Handle* h);                                 // backup Delta

@@ -90,6 +90,7 @@ struct LevelArgs {
   int n, B;
   double* D; const double* E; double* Zin; double* Zout; double* S;
   int* perm; int* nd; int* df; DeflRot* rots; int* kcnt; int* nrot; double* rho;
+  int* pos; int* ndc; int* kcls;     // class order of the non-deflated columns (top-only | mixed | bottom-only)
   double* dl; double* wv; double* dnew; double* zhat; double* stau; int* sorg;
   int* status;
   Mask mask;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) dc_prepare_kernel(LevelArgs g) {
   double* sd = reinterpret_cast<double*>(smem_raw);
   double* sz = sd + m;
   int* sord = reinterpret_cast<int*>(sz + m);
+  int* smix = sord + m;
   __shared__ double red[32];
   __shared__ int s_k, s_nrot;
 
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256) dc_prepare_kernel(LevelArgs g) {
     sd[i] = dv;
     sz[i] = zv;
     sord[i] = i;
+    smix[i] = 0;
     dmax = fmax(dmax, fabs(dv));
     zmax = fmax(zmax, fabs(zv));
   }
@@ -178,6 +181,25 @@ __global__ void __launch_bounds__(256) dc_prepare_kernel(LevelArgs g) {
     g.kcnt[vo] = k;
     g.nrot[vo] = nrot;
     g.rho[vo] = rho;
+    // The input eigenvector block is block diagonal (n1 x n1, n2 x n2); only columns touched by a
+    // rotation across the halves are dense.  Order the non-deflated columns top-only | mixed |
+    // bottom-only so the eigenvector GEMM can skip the zero half of every row tile.
+    for (int r = 0; r < nrot; ++r) {
+      const int a = rots[r].a, c2 = rots[r].b;
+      if (((a < n1) != (c2 < n1)) || smix[a] || smix[c2]) { smix[a] = 1; smix[c2] = 1; }
+    }
+    int cnt[3] = {0, 0, 0};
+    for (int q = 0; q < k; ++q) { const int j = nd[q]; cnt[smix[j] ? 1 : (j < n1 ? 0 : 2)]++; }
+    int start[3] = {0, cnt[0], cnt[0] + cnt[1]};
+    g.kcls[vo] = cnt[0];
+    g.kcls[vo + 1] = cnt[0] + cnt[1];
+    for (int q = 0; q < k; ++q) {
+      const int j = nd[q];
+      const int cls = smix[j] ? 1 : (j < n1 ? 0 : 2);
+      const int at = start[cls]++;
+      g.pos[vo + q] = at;
+      g.ndc[vo + at] = j;
+    }
   }
   __syncthreads();
   const int k = s_k, nrot = s_nrot;
@@ -328,7 +350,8 @@ __global__ void __launch_bounds__(256) dc_vectors_kernel(LevelArgs g) {
   for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
   const double sc = 1.0 / sqrt(nrm);
   double* Sc = g.S + (size_t)b * n * n + (size_t)(off + j) * n + off;
-  for (int i = lane; i < k; i += 32) Sc[i] = zh[i] / ((dl[i] - dorg) - tau) * sc;
+  const int* pos = g.pos + vo;
+  for (int i = lane; i < k; i += 32) Sc[pos[i]] = zh[i] / ((dl[i] - dorg) - tau) * sc;
 }
 
 // ---- Q_out[:, 0:k] = Q_in[:, nd[0:k]] * S[0:k, 0:k]  (real, DMMA m8n8k4) ------------------
@@ -361,18 +384,23 @@ __global__ void __launch_bounds__(256) dc_gemm2_kernel(GemmArgs ga) {
   const double* Qi = g.Zin + blk;
   const double* S = g.S + blk;
   double* Qo = g.Zout + blk;
-  const int* nd = g.nd + vo;
-  const int KT = (k + GBK - 1) / GBK;
+  const int* nd = g.ndc + vo;
+  // rows of the first input block see top-only and mixed columns, rows of the second mixed and bottom-only
+  const int n1 = g.n1[mi];
+  const int kT = g.kcls[vo], kTM = g.kcls[vo + 1];
+  const int kb = (m0 >= n1) ? kT : 0;
+  const int ke = (m0 + GBM <= n1) ? kTM : k;
+  const int KT = (ke - kb + GBK - 1) / GBK;
 
   auto load_tile = [&](int kt, int stage) {
-    const int k0 = kt * GBK;
+    const int k0 = kb + kt * GBK;
     double* As = smem + (size_t)stage * G_STAGE;
     double* Bs = As + GBK * GLDA;
 #pragma unroll
     for (int i = 0; i < (GBM * GBK) / 256; ++i) {
       const int idx = tid + i * 256;
       const int mm = idx % GBM, kk = idx / GBM;
-      const bool p = (m0 + mm < m) && (k0 + kk < k);
+      const bool p = (m0 + mm < m) && (k0 + kk < ke);
       const double* src = p ? Qi + (size_t)nd[k0 + kk] * n + (m0 + mm) : Qi;
       cp_async8(As + kk * GLDA + mm, src, p);
     }
@@ -380,7 +408,7 @@ __global__ void __launch_bounds__(256) dc_gemm2_kernel(GemmArgs ga) {
     for (int i = 0; i < (GBN * GBK) / 256; ++i) {
       const int idx = tid + i * 256;
       const int kk = idx % GBK, nn = idx / GBK;
-      const bool p = (n0 + nn < k) && (k0 + kk < k);
+      const bool p = (n0 + nn < k) && (k0 + kk < ke);
       const double* src = p ? S + (size_t)(n0 + nn) * n + (k0 + kk) : S;
       cp_async8(Bs + nn * GLDB + kk, src, p);
     }
@@ -524,13 +552,14 @@ int dw_stedc(Handle* h, Mask mask) {
     g.D = h->d; g.E = h->e; g.Zin = Zin; g.Zout = Zout; g.S = h->S;
     g.perm = h->perm; g.nd = h->ndl; g.df = h->dfl; g.rots = reinterpret_cast<DeflRot*>(h->rots);
     g.kcnt = h->kcnt; g.nrot = h->nrot; g.rho = h->rho;
+    g.pos = h->ord; g.ndc = h->ndc; g.kcls = h->kcls;
     g.dl = h->dl; g.wv = h->wv; g.dnew = h->dnew; g.zhat = h->zhat; g.stau = h->stau; g.sorg = h->sorg;
     g.status = h->status; g.mask = mask;
     const int mm = lv.max_m;
     if ((size_t)mm * 24 > 96 * 1024) { h->err = "dw_stedc: matrix too large"; return DWHMC_E_BADARG; }
     {
       dim3 grid(lv.nmerge, B);
-      dc_prepare_kernel<<<grid, 256, (size_t)mm * 20 + 16, h->stream>>>(g);
+      dc_prepare_kernel<<<grid, 256, (size_t)mm * 24 + 16, h->stream>>>(g);
       DW_LAUNCH_CHECK(h);
     }
     {

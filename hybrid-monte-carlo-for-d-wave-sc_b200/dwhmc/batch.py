@@ -125,6 +125,15 @@ class ChainBatch:
     def seed(self, seed: int):
         check(lib.dwhmc_seed(self._h, C.c_uint64(seed)), self._h)
 
+    def init_state(self, W, n_imp):
+        """initialize_state (src/Types.jl:118-134) for every chain on the device (Philox stream of seed())."""
+        check(lib.dwhmc_init_state(self._h, dptr(_vec(W, self.B)), dptr(_vec(n_imp, self.B))), self._h)
+
+    def get_disorder(self):
+        out = np.empty((self.B, self.N))
+        check(lib.dwhmc_get_disorder(self._h, dptr(out)), self._h)
+        return out
+
     # ---- operators (1:1 with the reference)
     def init_static_H(self):
         check(lib.dwhmc_init_static_H(self._h), self._h)

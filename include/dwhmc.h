@@ -71,6 +71,7 @@ int dwhmc_set_params(dwhmc_handle h, const double* t, const double* tp, const do
                      const double* beta, const double* J, const double* mass);
 /* SimulationState.disorder_pot (src/Types.jl:104): double[N * B]. */
 int dwhmc_set_disorder(dwhmc_handle h, const double* w);
+int dwhmc_get_disorder(dwhmc_handle h, double* w);
 /* SimulationState.Delta (src/Types.jl:111): complex[N * 2 * B]. */
 int dwhmc_set_field(dwhmc_handle h, const double* delta);
 int dwhmc_get_field(dwhmc_handle h, double* delta);
@@ -80,6 +81,11 @@ int dwhmc_get_momentum(dwhmc_handle h, double* pi);
 /* seed of the on-device Philox generator used when momenta / uniforms are not
  * injected (throughput mode; the reference uses Julia's unseeded task RNG). */
 int dwhmc_seed(dwhmc_handle h, uint64_t seed);
+/* initialize_state(p) src/Types.jl:118-134 for every chain, on the device (Philox stream of dwhmc_seed):
+ * disorder = W[b] on round(N * n_imp[b]) distinct uniformly random sites (0 elsewhere), Delta0 with
+ * Re, Im ~ U[-0.05, 0.05), pi = 0.  W, n_imp: double[B].  (Parity runs inject host-drawn state through
+ * dwhmc_set_disorder / dwhmc_set_field instead.) */
+int dwhmc_init_state(dwhmc_handle h, const double* W, const double* n_imp);
 
 /* ---- per-operator entry points (1:1 with the reference operators) ------- */
 

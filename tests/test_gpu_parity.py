@@ -498,6 +498,38 @@ def test_device_rng_statistics(dw):
     cb.close()
 
 
+def test_device_initialize_state(dw):
+    """initialize_state on the device (src/Types.jl:118-134): round(N n_imp) distinct impurity sites at W
+    (Julia round = ties to even), Delta0 with Re, Im ~ U[-0.05, 0.05), pi = 0; chains differ; reseeding
+    reproduces the draw."""
+    B, L = 32, 10
+    N = L * L
+    cb = dw.ChainBatch(B, L, L)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], 5.0, PHYS["J"], 1.0)
+    n_imp = np.where(np.arange(B) % 2 == 0, 0.078, 0.025)       # 7.8 -> 8 sites, 2.5 -> 2 sites (ties to even)
+    cb.seed(77)
+    cb.init_state(3.0, n_imp)
+    w, d, pi = cb.get_disorder(), cb.get_field(), cb.get_momentum()
+    for b in range(B):
+        assert set(np.unique(w[b])) <= {0.0, 3.0}
+        assert np.count_nonzero(w[b]) == int(np.rint(N * n_imp[b]))
+    assert np.all(pi == 0)
+    x = np.concatenate([d.real.ravel(), d.imag.ravel()])
+    assert x.min() >= -0.05 and x.max() < 0.05
+    assert abs(x.mean()) < 2e-3 and abs(x.var() - 0.01 / 12) < 1e-4
+    assert len({tuple(np.flatnonzero(w[b])) for b in range(0, B, 2)}) > B // 4          # chains differ
+    hits = np.zeros(N)
+    for b in range(B):
+        hits += w[b] != 0
+    assert hits.max() <= 8                                                           # no preferred site
+    cb.seed(77)
+    cb.init_state(3.0, n_imp)
+    assert np.array_equal(cb.get_disorder(), w) and np.array_equal(cb.get_field(), d)
+    cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG()
+    assert np.all(np.isfinite(cb.measure_observables()))
+    cb.close()
+
+
 def test_batched_run_driver_matches_oracle_run(dw, tmp_path):
     """run_simulation (src/Simulation.jl:34-236) for two chains at once, host-RNG mode: the adaptive
     thermalisation decisions, accept flags, dH and the nine observables of every measured sweep equal
