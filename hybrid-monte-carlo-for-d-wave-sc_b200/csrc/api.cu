@@ -154,7 +154,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   AL(h->Ppart, (size_t)h->fchunks * nB); AL(h->hpart, (size_t)h->fchunks * B); AL(h->Pbond, nB);
   AL(h->A, nnB); AL(h->V, nnB);
   AL(h->ypart, (size_t)((n + 63) / 64) * nB); AL(h->P1, (size_t)DW_CC * DW_NB * B); AL(h->P2, (size_t)DW_CC * DW_NB * B);
-  AL(h->Tf, (size_t)h->nbt * DW_NBT * DW_NBT * B); AL(h->Gb, (size_t)h->nbt * DW_NBT * DW_NBT * B); AL(h->tau, nB); AL(h->d, nB); AL(h->e, nB);
+  AL(h->Tf, (size_t)h->nbt * DW_NBT * DW_NBT * B); AL(h->Gb, (size_t)h->nbt * DW_NBT * DW_NBT * B * DW_GSPLIT); AL(h->tau, nB); AL(h->d, nB); AL(h->e, nB);
   AL(h->Wbt, (size_t)DW_NBT * nB); AL(h->Wbt2, (size_t)DW_NBT * nB);
   AL(h->Z0, nnB); AL(h->Z1, nnB); AL(h->S, nnB);
   AL(h->perm, nB); AL(h->ord, nB);

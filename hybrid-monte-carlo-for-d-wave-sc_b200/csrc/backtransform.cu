@@ -18,7 +18,8 @@ __device__ __forceinline__ void cfma_(cplx& acc, cplx a, cplx b) {
 // T[i,i] = tau_i, T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i].  Thread r owns row r of T, which only
 // depends on earlier entries of the same row, so the recurrence needs no barrier.
 __global__ void __launch_bounds__(DW_NBT) bt_larft_kernel(const cplx* __restrict__ tau, const cplx* __restrict__ Gall,
-                                                          cplx* __restrict__ Tall, int n, int nbt, Mask mask) {
+                                                          cplx* __restrict__ Tall, int n, int nbt, size_t gsplit_stride,
+                                                          Mask mask) {
   const int k = blockIdx.x, b = blockIdx.y;
   if (!mask.on(b)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -29,7 +30,12 @@ __global__ void __launch_bounds__(DW_NBT) bt_larft_kernel(const cplx* __restrict
   const int pn = min(DW_NBT, n - 1 - j0);
   const cplx* Gk = Gall + ((size_t)b * nbt + k) * DW_NBT * DW_NBT;
   for (int c = 0; c < DW_NBT; ++c) {
-    G[c * DW_NBT + r] = Gk[c * DW_NBT + r];
+    cplx gs = Gk[c * DW_NBT + r];
+    for (int sp = 1; sp < DW_GSPLIT; ++sp) {        // K pieces of the Gram GEMM, fixed order
+      const cplx t = Gk[(size_t)sp * gsplit_stride + c * DW_NBT + r];
+      gs.x += t.x; gs.y += t.y;
+    }
+    G[c * DW_NBT + r] = gs;
     T[r * (DW_NBT + 1) + c] = make_double2(0.0, 0.0);
   }
   __syncthreads();
@@ -91,10 +97,13 @@ int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
     a.M = pn; a.N = pn; a.K = mk;
     a.A[0] = Vk; a.lda = n; a.sA = (long long)n * n; a.opA = 1;
     a.Bm[0] = Vk; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
+    // long K, tiny output: cut K into DW_GSPLIT pieces so the launch fills the machine; bt_larft_kernel sums them
     a.C = h->Gb + (size_t)k * DW_NBT * DW_NBT; a.ldc = DW_NBT; a.sC = sT;
+    a.ksplit = DW_GSPLIT; a.sCk = sT * B;
     a.alpha = 1.0; a.beta = 0.0;
     DW_TRY(dw_zgemm(h, a));
   }
+  a.ksplit = 1; a.sCk = 0;
   {
     static bool attr_set[64] = {false};
     const size_t smem = sizeof(cplx) * (DW_NBT * (DW_NBT + 1) + DW_NBT * DW_NBT);
@@ -103,7 +112,7 @@ int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
       attr_set[h->device & 63] = true;
     }
     dim3 grid(nbt, B);
-    bt_larft_kernel<<<grid, DW_NBT, smem, h->stream>>>(h->tau, h->Gb, h->Tf, n, nbt, mask);
+    bt_larft_kernel<<<grid, DW_NBT, smem, h->stream>>>(h->tau, h->Gb, h->Tf, n, nbt, (size_t)sT * B, mask);
     DW_LAUNCH_CHECK(h);
   }
   for (int k = nbt - 1; k >= 0; --k) {

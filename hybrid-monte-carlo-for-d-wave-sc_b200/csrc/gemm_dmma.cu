@@ -14,14 +14,19 @@ using namespace dwg;
 namespace {
 
 constexpr int BK = 16;
-constexpr int STAGES = 3;
 constexpr int NTHREADS = 256;
+
+#ifndef GEMM_CN_STAGES
+#define GEMM_CN_STAGES 2
+#endif
 
 template <int BM, int BN, int OPA, int OPB>
 struct Tile {
   static constexpr int A_ELEMS = (OPA == 0) ? BK * (BM + 2) : BM * (BK + 4);
   static constexpr int B_ELEMS = (OPB == 0) ? BN * (BK + 4) : BK * (BN + 2);
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  // three cp.async stages, except for the 64x64 (C, N) tile whose 40 KB stages would leave only one CTA per SM
+  static constexpr int STAGES = (OPA == 1 && OPB == 0 && BM == 64 && BN == 64) ? GEMM_CN_STAGES : 3;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_ELEMS * sizeof(cplx);
 };
 
@@ -38,6 +43,8 @@ struct KArgs {
   const int* skip_flag;
   int skip_cols;
   int stairA;
+  int ksplit;
+  long long sCk;
 };
 
 // two CTAs per SM whenever the tile's shared memory allows it (<= 128 registers per thread)
@@ -45,13 +52,14 @@ template <int BM, int BN, int WM, int WN, int OPA, int OPB>
 __global__ void __launch_bounds__(NTHREADS, (Tile<BM, BN, OPA, OPB>::SMEM <= 113 * 1024) ? 2 : 1)
 zgemm_dmma_kernel(KArgs g) {
   using T = Tile<BM, BN, OPA, OPB>;
+  constexpr int STAGES = T::STAGES;
   constexpr int WTM = BM / WM, WTN = BN / WN;   // warp tile
   constexpr int MI = WTM / 8, NI = WTN / 8;
   static_assert(WM * WN * 32 == NTHREADS, "8 warps");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* smem = reinterpret_cast<cplx*>(smem_raw);
 
-  const int b = g.b0 + blockIdx.z;
+  const int b = g.b0 + blockIdx.z / g.ksplit;
   if (!g.mask.on(b)) return;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (g.lower && n0 > m0 + BM - 1) return;
@@ -64,6 +72,15 @@ zgemm_dmma_kernel(KArgs g) {
   const cplx* Bseg0 = g.B0 + (size_t)b * g.sB;
   const cplx* Bseg1 = g.B1 ? g.B1 + (size_t)b * g.sB : Bseg0;
   cplx* C = g.C + (size_t)b * g.sC;
+  if (g.ksplit > 1) {          // this CTA's piece of the K range (single segment only)
+    const int ks = blockIdx.z % g.ksplit;
+    const int kc = ((g.K + g.ksplit - 1) / g.ksplit + BK - 1) / BK * BK;
+    const int kbeg = min(g.K, ks * kc);
+    Aseg0 += (OPA == 0) ? (size_t)kbeg * g.lda : (size_t)kbeg;
+    Bseg0 += (OPB == 0) ? (size_t)kbeg : (size_t)kbeg * g.ldb;
+    g.K = min(kc, g.K - kbeg);
+    C += (size_t)ks * g.sCk;
+  }
 
   const int KTS = (g.K + BK - 1) / BK;   // k-tiles per segment
   const int KT = KTS * g.nseg;
@@ -231,7 +248,8 @@ int launch(Handle* h, const ZgemmArgs& a) {
   g.sA = a.sA; g.sB = a.sB; g.sC = a.sC;
   g.C = a.C; g.alpha = a.alpha; g.beta = a.beta; g.lower = a.lower; g.mask = a.mask; g.b0 = a.b0;
   g.skip_flag = a.skip_flag; g.skip_cols = a.skip_cols; g.stairA = a.stairA;
-  dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
+  g.ksplit = a.ksplit > 1 ? a.ksplit : 1; g.sCk = a.sCk;
+  dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch * g.ksplit);
   static int pad = -1;                  // DWHMC_GEMM_PAD=KB: extra dynamic smem (experiment: limit CTAs/SM)
   if (pad < 0) {
     const char* e = getenv("DWHMC_GEMM_PAD"); pad = e ? atoi(e) * 1024 : 0;

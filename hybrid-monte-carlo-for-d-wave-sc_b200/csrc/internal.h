@@ -15,6 +15,10 @@
 #define DW_CC 4
 #endif
 //      DW_CC:           // CTAs per cluster in the column-step kernel
+#ifndef DW_GSPLIT
+#define DW_GSPLIT 8
+#endif
+// DW_GSPLIT: K pieces of the Gram-matrix GEMMs of the back-transformation
 #define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
 #define DW_LEAF 36        // largest D&C leaf
 #define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
@@ -208,6 +212,8 @@ struct ZgemmArgs {
   int batch;
   Mask mask;
   int b0 = 0;                  // first chain of the launch (chain groups)
+  int ksplit = 1;              // > 1: the K range is cut into ksplit pieces, piece s of chain b writes its partial
+  long long sCk = 0;           //   product to C + b * sC + s * sCk (beta must be 0; the consumer sums the pieces)
   int stairA = 0;              // > 0: the A operand is a staircase block: entry (row r, column c) of the
                                //   source is used only if 0 <= r - c < stairA (band.cu block reflectors)
   const int* skip_flag = nullptr;  // device [B] or null: chains with flag != 0 skip the column tiles that

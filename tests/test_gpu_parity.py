@@ -383,6 +383,45 @@ def test_transport_golden_vectors(dw, path):
     cache.batch.close()
 
 
+def test_transport_full_size_and_errors(dw):
+    """BASELINE config 3 size (L = 24, n = 1152, 1436 frequencies): one chain against the oracle, the second chain
+    through size-independent properties (sigma >= 0, DOS sum rule, A(k,0) Parseval); argument errors."""
+    L = 24
+    betas = [20.0, 1000.0]
+    cb, ps, sts, cs = make_batch(dw, L, betas, 0.05, 1700)
+    N = L * L
+    eta = 8.0 / N
+    cb.measure_observables()
+    r = cb.measure_transport_and_spectra(eta, 0.2 * eta, 4.0)
+    p = ps[0]
+    p.eta, p.d_omega, p.omega_max = eta, 0.2 * eta, 4.0
+    orc.measure_observables(cs[0], p, sts[0])
+    ref = orc.measure_transport_and_spectra(cs[0], p)
+    assert abs(r["superfluid_stiffness"][0] - ref.superfluid_stiffness) <= 1e-9
+    assert abs(r["dc_conductivity"][0] - ref.dc_conductivity) <= 1e-9 * max(abs(ref.dc_conductivity), 1e-6)
+    for key, arr in (("optical_conductivity", ref.optical_conductivity), ("dos", ref.dos), ("dos_AN", ref.dos_AN),
+                     ("A_k_w0", ref.A_k_w0)):
+        assert np.max(np.abs(r[key][0] - arr)) <= 1e-9 * max(np.max(np.abs(arr)), 1e-12), key
+    E, U = cb.get_eigenvalues()[1], cb.get_eigenvectors()[1].T
+    w_n = np.sum(np.abs(U[:N]) ** 2, axis=0)
+    assert np.all(r["optical_conductivity"][1] >= -1e-12) and np.all(r["dos_AN"][1] >= 0)
+    # DOS sum rule: the integral over the window equals the Lorentzian weight of every state inside it
+    inside = (np.arctan((4.0 - E) / eta) - np.arctan((-4.0 - E) / eta)) / np.pi
+    assert abs(np.sum(r["dos"][1]) * 0.2 * eta - np.sum(w_n * inside) / N) <= 2e-3
+    w0 = orc.lorentzian(-E, eta)
+    sel = w0 > 1e-6
+    assert abs(np.sum(r["A_k_w0"][1]) - np.sum(w_n[sel] * w0[sel])) <= 1e-9 * max(np.sum(r["A_k_w0"][1]), 1.0)
+    with pytest.raises(dw.DwhmcError):
+        cb.measure_transport_and_spectra(0.0, 0.1, 4.0)                 # eta must be positive
+    with pytest.raises(dw.DwhmcError):
+        cb.init_state(1.0, 1.5)                                         # n_imp outside [0, 1]
+    cb.trajectory(2, 0.01)
+    with pytest.raises(dw.DwhmcError):
+        cb.measure_transport_and_spectra(eta, 0.2 * eta, 4.0)           # proposal pending
+    cb.commit(np.ones(2, int))
+    cb.close()
+
+
 def test_transport_single_chain_api(dw):
     """Reads like the reference: measure_observables, then measure_transport_and_spectra(cache, p)."""
     p = dw.ModelParameters(8, 8, 1.0, -0.35, -1.08, 1.0, 0.05, 20.0, 0.8, 1.0, eta=0.125, d_omega=0.025, omega_max=4.0)
