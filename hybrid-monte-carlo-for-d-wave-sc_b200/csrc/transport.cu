@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(256) pair_static_kernel(const cplx* __restrict
   }
 }
 
-// Re sigma(omega_k) partial sums: CTA = (256 frequencies, chunk of PCH columns m, chain); the pairs of the
-// chunk are staged in shared memory as (E_m - E_n, (f_n - f_m) |J_nm|^2) and broadcast to the threads.
+// Re sigma(omega_k) partial sums: CTA = (256 frequencies, chunk of PCH columns m, chain).  The pairs of the
+// chunk with |f_n - f_m| >= 1e-12 (src/Observables.jl:415) are compacted (deterministic block scan, original
+// order kept) into shared memory as (E_m - E_n, (f_n - f_m) |J_nm|^2) and broadcast to the threads.  Four terms
+// share one division:  sum_i w_i / d_i = (N12 P34 + N34 P12) / (P12 P34),  d_i = (omega - Delta_i)^2 + eta^2
+// (d_i in [eta^2, ~100], so the products stay far inside the FP64 range).
 constexpr int PCH = 4;          // columns m per CTA -> 4 n pairs
 __global__ void __launch_bounds__(256) sigma_partial_kernel(const double* __restrict__ J2all, const double* __restrict__ Eall,
                                                             const double* __restrict__ fall, const double* __restrict__ omega,
@@ -152,39 +155,71 @@ __global__ void __launch_bounds__(256) sigma_partial_kernel(const double* __rest
                                                             double eta) {
   const int b = blockIdx.z, chunk = blockIdx.y;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* pr = reinterpret_cast<double2*>(smem_raw);       // [PCH * n] (delta, weight)
+  double2* pr = reinterpret_cast<double2*>(smem_raw);       // [PCH * n + 4] (delta, weight), compacted
+  __shared__ int wsum[8];
+  __shared__ int s_tot;
   const double* E = Eall + (size_t)b * n;
   const double* f = fall + (size_t)b * n;
   const double* J2 = J2all + (size_t)b * n * n;
   const int m0 = chunk * PCH;
-  __syncthreads();
-  // keep only pairs with |f_n - f_m| >= 1e-12 (src/Observables.jl:415); order inside a chunk is irrelevant
-  // for parity at the 1e-13 level but is made deterministic by a fixed slot = index (zero weight when skipped)
-  for (int idx = threadIdx.x; idx < PCH * n; idx += blockDim.x) {
+  const int tot_in = PCH * n;
+  const int per = (tot_in + 255) / 256;                     // contiguous slice per thread keeps the order
+  const int lo = threadIdx.x * per, hi = min(tot_in, lo + per);
+  int cnt = 0;
+  for (int idx = lo; idx < hi; ++idx) {
     const int mm = m0 + idx / n, r = idx % n;
-    double2 v = make_double2(0.0, 0.0);
+    if (mm < n && fabs(f[r] - f[mm]) >= 1e-12) ++cnt;
+  }
+  // exclusive scan of cnt over the block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int w8 = 0; w8 < warp; ++w8) base += wsum[w8];
+  if (threadIdx.x == 255) s_tot = base + inc;
+  int at = base + inc - cnt;
+  for (int idx = lo; idx < hi; ++idx) {
+    const int mm = m0 + idx / n, r = idx % n;
     if (mm < n) {
       const double df = f[r] - f[mm];
-      if (fabs(df) >= 1e-12) v = make_double2(E[mm] - E[r], df * J2[(size_t)mm * n + r]);
+      if (fabs(df) >= 1e-12) pr[at++] = make_double2(E[mm] - E[r], df * J2[(size_t)mm * n + r]);
     }
-    pr[idx] = v;
   }
+  __syncthreads();
+  const int tot = s_tot;
+  const int tot4 = (tot + 3) & ~3;
+  if (threadIdx.x < tot4 - tot) pr[tot + threadIdx.x] = make_double2(0.0, 0.0);     // neutral padding
   __syncthreads();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const double w = (k < nw) ? omega[k] : 1.0;
   const double eta2 = eta * eta;
-  double acc = 0.0;
-  const int tot = PCH * n;
-#pragma unroll 4
-  for (int idx = 0; idx < tot; ++idx) {
-    const double2 v = pr[idx];
-    if (v.y != 0.0) {
-      const double x = w - v.x;
-      acc += v.y / (x * x + eta2);
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int idx = 0; idx < tot4; idx += 8) {
+    {
+      const double2 v0 = pr[idx], v1 = pr[idx + 1], v2 = pr[idx + 2], v3 = pr[idx + 3];
+      const double x0 = w - v0.x, x1 = w - v1.x, x2 = w - v2.x, x3 = w - v3.x;
+      const double d0 = fma(x0, x0, eta2), d1 = fma(x1, x1, eta2), d2 = fma(x2, x2, eta2), d3 = fma(x3, x3, eta2);
+      const double p01 = d0 * d1, p23 = d2 * d3;
+      const double n01 = fma(v0.y, d1, v1.y * d0), n23 = fma(v2.y, d3, v3.y * d2);
+      acc0 += fma(n01, p23, n23 * p01) / (p01 * p23);
+    }
+    if (idx + 4 < tot4) {
+      const double2 v0 = pr[idx + 4], v1 = pr[idx + 5], v2 = pr[idx + 6], v3 = pr[idx + 7];
+      const double x0 = w - v0.x, x1 = w - v1.x, x2 = w - v2.x, x3 = w - v3.x;
+      const double d0 = fma(x0, x0, eta2), d1 = fma(x1, x1, eta2), d2 = fma(x2, x2, eta2), d3 = fma(x3, x3, eta2);
+      const double p01 = d0 * d1, p23 = d2 * d3;
+      const double n01 = fma(v0.y, d1, v1.y * d0), n23 = fma(v2.y, d3, v3.y * d2);
+      acc1 += fma(n01, p23, n23 * p01) / (p01 * p23);
     }
   }
   // (fn_fm / w) J2 (1/pi) eta / (x^2 + eta^2)
-  if (k < nw) spart[((size_t)b * nchunk + chunk) * nw + k] = acc * (eta / PI) / w;
+  if (k < nw) spart[((size_t)b * nchunk + chunk) * nw + k] = (acc0 + acc1) * (eta / PI) / w;
 }
 
 __global__ void sigma_reduce_kernel(const double* __restrict__ spart, double* __restrict__ sigma, int nw, int nchunk,
@@ -354,7 +389,7 @@ int dw_transport(Handle* h, double eta, const double* omega_dev, int nw, const d
   transport_scalar_kernel<<<B, 256, 0, h->stream>>>(h->E_cur, wts, part, h->par, scal, n, N, B);
   DW_LAUNCH_CHECK(h);
   if (nw > 0) {
-    const size_t smem = sizeof(double2) * (size_t)PCH * n;
+    const size_t smem = sizeof(double2) * ((size_t)PCH * n + 4);
     static bool attr_set[64] = {false};
     if (!attr_set[h->device & 63]) {
       DW_CUDA(h, cudaFuncSetAttribute(sigma_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
