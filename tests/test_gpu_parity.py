@@ -296,6 +296,32 @@ def test_particle_hole_shortcut_and_fallback(dw, monkeypatch):
     cb.close()
 
 
+@pytest.mark.parametrize("L,B", [((6, 10), 3), ((10, 6), 2), (8, 150)])
+def test_band_route_shapes(dw, monkeypatch, L, B):
+    """Band route on rectangular lattices (the short ring is the fast index of the fold ordering either way) and on
+    a batch larger than one cooperative launch of the chase kernel can hold (148 CTAs): spectrum and correlators
+    equal the dense route's."""
+    Lx, Ly = (L, L) if isinstance(L, int) else L
+    N = Lx * Ly
+    rng = np.random.default_rng(31)
+    betas = np.linspace(2.0, 50.0, B)
+    w = np.zeros((B, N)); w[:, rng.permutation(N)[:3]] = 1.0
+    delta = (rng.random((B, 2, N)) - 0.5 + 1j * (rng.random((B, 2, N)) - 0.5)) * 0.2
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DWHMC_BAND", mode)
+        cb = dw.ChainBatch(B, Lx, Ly)
+        cb.set_params(1.0, -0.35, -1.08, betas, 0.8, 1.0)
+        cb.set_disorder(w); cb.set_field(delta)
+        cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG(); cb.compute_forces()
+        res[mode] = (cb.get_eigenvalues(), cb.get_forces(), cb.measure_observables())
+        cb.close()
+    monkeypatch.delenv("DWHMC_BAND")
+    assert np.max(np.abs(res["1"][0] - res["0"][0])) <= 1e-12 * np.max(np.abs(res["0"][0]))
+    assert rel(res["1"][1], res["0"][1]) <= 1e-11
+    assert np.allclose(res["1"][2], res["0"][2], rtol=1e-10, atol=1e-12)
+
+
 def test_band_route_matches_dense_route(dw, monkeypatch):
     """DWHMC_BAND=1: BdG matrix assembled straight into band storage (folded site order, half-bandwidth
     4L+4), bulge-chased to tridiagonal form, block-reflector back-transformation.  Same spectrum,
