@@ -134,7 +134,7 @@ struct Handle {
   // transport / spectra workspace (transport.cu), allocated on first use
   double* tr_work = nullptr; size_t tr_work_count = 0;
   double* tr_out = nullptr; size_t tr_out_count = 0;     // scal | sigma | dos | dosAN | ak | omega | dosgrid
-  int ngroups = 2;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
+  int ngroups = 3;              // chain groups in use (env DWHMC_NGROUP, 1..DW_NGROUP)
   // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
   // upper half of the spectrum are back-transformed, the rest are their conjugate partners
   int nsm = 148;                // SMs of the device
