@@ -114,3 +114,23 @@ def test_run_driver_formats_and_adaptive_Nt(built):
     assert sim.scan_dir_T(Ts[0]) == "T_0.0001" and sim.scan_dir_T(Ts[-1]) == "T_1000.0"
     assert sim.scan_dir_T(Ts[1]) == "T_0.000202"
     assert sim.scan_dir_beta(0.01) == "beta_0.01" and sim.scan_dir_beta(100000.0) == "beta_100000.0"
+
+
+def test_bench_reference_arm_contract(built):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints exactly one JSON line on
+    stdout with the contract's keys; small lattice so the CPU suite stays fast."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--L", "4", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "trajectories/s" and d["dtype"] == "f64" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
