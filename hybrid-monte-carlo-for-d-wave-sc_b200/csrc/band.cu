@@ -695,6 +695,329 @@ constexpr size_t chase_fast_smem() {
   return sizeof(cplx) * ((size_t)(TB | 1) * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * TB + 32);
 }
 
+// ---- TMA variant of the register-blocked chase kernel -------------------------------------------------
+// The two b x b block transfers of a step go through the bulk-copy engine instead of the load/store units:
+// the carried block is updated in place in shared memory and written back with one cp.async.bulk per column
+// (shared -> global, bulk group), the next block is fetched with one cp.async.bulk per column (global ->
+// shared, mbarrier complete_tx).  The store overlaps the diagonal-block products, the load overlaps the
+// diagonal-block update.  The diagonal block itself stays in registers (4 x 5 sub-block per thread); its
+// Hermitian product needs a row and a column reduction.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int TB, int TR, int TC, int RB, int CB>
+__global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
+  static_assert(TR * RB == TB && TC * CB == TB && TR * TC <= CT && TB <= CT, "exact cover");
+  constexpr int LDB = TB | 1;
+  constexpr int LD = 2 * TB;
+  constexpr int NP = (TR > TC) ? TR : TC;
+  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
+  if (!g.mask.on(chain)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = g.n;
+  cplx* Bc = reinterpret_cast<cplx*>(smem_raw);      // [TB][LDB]
+  cplx* vs = Bc + LDB * TB;
+  cplx* vp = vs + TB;
+  cplx* us = vp + TB;
+  cplx* xs = us + TB;
+  cplx* tu = xs + TB;
+  cplx* wc = tu + TB;
+  cplx* part = wc + TB;                              // [NP][TB]
+  cplx* red = part + NP * TB;                        // [32]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
+  const int tid = threadIdx.x;
+  const bool act = tid < TR * TC;
+  const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
+  const int soff = cj * LDB + ri;
+  const int goff = cj * (LD - 1) + ri;
+  cplx* AB = g.AB + (size_t)chain * n * LD;
+  cplx* V = g.V + (size_t)chain * n * n;
+  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
+  int* prog = g.prog + (size_t)chain * n;
+  const cplx zero = make_double2(0.0, 0.0);
+  if (tid == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned ephase = 0;                               // parity of the next-block barrier
+  bool store_pending = false;
+
+  for (int s = p; s < n - 1; s += g.P) {
+    int k = 0, r0 = s + 1;
+    cplx taup = zero;
+    int lcar = 0;                                    // rows of the carried block in flight / in Bc
+    while (true) {
+      const int ln = min(TB, n - r0);
+      if (k > 0) {
+        // the carried block (issued at the end of the previous step) must have landed; u = Bn vp
+        mbar_wait(bar, ephase);
+        ephase ^= 1;
+        if (act) {
+          cplx acc[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            const cplx vj = vp[cj + cc * TC];
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR < lcar) cfma(acc[q], Bc[soff + cc * TC * LDB + q * TR], vj);
+          }
+#pragma unroll
+          for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
+        }
+        __syncthreads();
+        for (int i = tid; i < lcar; i += CT) {
+          cplx u = part[i];
+#pragma unroll 5
+          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * TB + i]);
+          us[i] = u;
+        }
+        __syncthreads();
+      }
+      if (k > 0 && ln <= 1) {
+        for (int idx = tid; idx < ln * TB; idx += CT) {
+          const int i = idx % ln, j = idx / ln;
+          cplx a = Bc[j * LDB + i];
+          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
+          stg2(AB + (size_t)(r0 - TB + j) * LD + (TB + i - j), a);
+        }
+        for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
+        break;
+      }
+      if (s > 0) {
+        if (tid == 0) {
+          const int need = k + 3;
+          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
+        }
+        __syncthreads();
+      }
+      // ---- prefetch the lower triangle of the diagonal block into registers
+      cplx* baseD = AB + (size_t)r0 * LD + goff;
+      cplx dreg[RB][CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c)
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          const int i = ri + q * TR, j = cj + c * TC;
+          dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
+        }
+      // ---- A. column to annihilate
+      if (k == 0) {
+        for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
+      } else {
+        for (int i = tid; i < ln; i += CT) {
+          const cplx t = cmul(taup, us[i]);
+          tu[i] = t;
+          xs[i] = csub(Bc[i], t);
+        }
+      }
+      __syncthreads();
+      // ---- B. reflector
+      cplx tau; double beta;
+      larfg_block(xs, vs, ln, red, tau, beta);
+      for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
+      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
+      cplx vr[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) vr[q] = (ri + q * TR < ln) ? vs[ri + q * TR] : zero;
+      if (k == 0) {
+        for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
+      } else {
+        // ---- C. carried block, updated in place, then written back by the bulk-copy engine
+        cplx c = zero;
+        for (int i = tid; i < ln; i += CT) cfmac(c, vs[i], tu[i]);
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
+            part[ri * TB + cj + cc * TC] = acc;
+          }
+        }
+        c = block_sum(c, red);
+        const cplx ctau = cconj(tau);
+        for (int j = tid; j < TB; j += CT) {
+          cplx z = part[j];
+#pragma unroll 5
+          for (int q = 1; q < TR; ++q) z = cadd(z, part[q * TB + j]);
+          cfms(z, c, cconj(vp[j]));
+          wc[j] = cmul(ctau, z);
+        }
+        __syncthreads();
+        if (act) {
+          cplx tur[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) tur[q] = tu[min(ri + q * TR, TB - 1)];
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            const int j = cj + cc * TC;
+            const cplx cvp = cconj(vp[j]), wj = wc[j];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+              const int i = ri + q * TR;
+              if (i < ln) {
+                cplx o = Bc[soff + cc * TC * LDB + q * TR];
+                cfms(o, tur[q], cvp);
+                cfms(o, vr[q], wj);
+                if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
+                Bc[soff + cc * TC * LDB + q * TR] = o;
+              }
+            }
+          }
+        }
+        fence_async();                                // generic-proxy writes of Bc -> visible to the bulk engine
+        __syncthreads();
+        if (tid < TB) {
+          cplx* dst = AB + (size_t)(r0 - TB + tid) * LD + (TB - tid);
+          bulk_s2g(dst, Bc + tid * LDB, (unsigned)(ln * sizeof(cplx)));
+          bulk_commit();
+        }
+        store_pending = true;
+      }
+      // ---- D. diagonal block from registers: x = tau D v, D Hermitian (lower part held)
+      {
+        // row part: sum_{j <= i} D[i,j] v[j]
+        if (act) {
+          cplx acc[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            const int j = cj + cc * TC;
+            const cplx vj = (j < ln) ? vs[j] : zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+              cplx a = dreg[q][cc];
+              if (ri + q * TR == j) a.y = 0.0;
+              cfma(acc[q], a, vj);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
+        }
+        __syncthreads();
+        for (int i = tid; i < ln; i += CT) {
+          cplx wv = part[i];
+#pragma unroll 5
+          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * TB + i]);
+          xs[i] = wv;
+        }
+        __syncthreads();
+        // column part: sum_{i > j} conj(D[i,j]) v[i]
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            const int j = cj + cc * TC;
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
+            part[ri * TB + j] = acc;
+          }
+        }
+        __syncthreads();
+        cplx dot = zero;
+        for (int i = tid; i < ln; i += CT) {
+          cplx wv = xs[i];
+#pragma unroll 5
+          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * TB + i]);
+          wv = cmul(tau, wv);
+          xs[i] = wv;
+          cfmac(dot, wv, vs[i]);
+        }
+        dot = block_sum(dot, red);
+        cplx alpha = cmul(tau, dot);
+        alpha.x *= -0.5; alpha.y *= -0.5;
+        for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
+        __syncthreads();
+      }
+      // ---- next block: fetch with the bulk engine while the diagonal block is updated and stored
+      const int r1 = r0 + ln;
+      const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
+      if (store_pending) {
+        if (tid < TB) bulk_wait_read();               // the write-back has finished reading Bc
+        __syncthreads();
+      }
+      if (l2 > 0) {
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)(l2 * sizeof(cplx)) * TB);
+        __syncthreads();
+        if (tid < TB) {
+          fence_async();
+          const cplx* src = AB + (size_t)(r0 + tid) * LD + (TB - tid);
+          bulk_g2s(Bc + tid * LDB, src, (unsigned)(l2 * sizeof(cplx)), bar);
+        }
+      }
+      // ---- D update and store (lower part, from registers)
+      if (act) {
+        cplx wr[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) wr[q] = xs[min(ri + q * TR, TB - 1)];
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          const int j = cj + cc * TC;
+          const cplx cwj = cconj(xs[j]), cvj = cconj(vs[j]);
+#pragma unroll
+          for (int q = 0; q < RB; ++q) {
+            const int i = ri + q * TR;
+            if (i >= j && i < ln) {
+              cplx a = dreg[q][cc];
+              if (i == j) a.y = 0.0;
+              cfms(a, vr[q], cwj);
+              cfms(a, wr[q], cvj);
+              if (i == j) a.y = 0.0;
+              stg2(baseD + cc * TC * (LD - 1) + q * TR, a);
+            }
+          }
+        }
+      }
+      if (store_pending) {
+        if (tid < TB) bulk_wait_all();                // write-back performed in global memory
+        store_pending = false;
+      }
+      if (l2 == 0) break;
+      for (int i = tid; i < ln; i += CT) vp[i] = vs[i];
+      taup = tau;
+      lcar = l2;
+      __syncthreads();
+      if (tid == 0) { fence_async(); __threadfence(); st_release(prog + s, k + 1); }
+      r0 = r1;
+      ++k;
+    }
+    __syncthreads();
+    if (tid == 0) { fence_async(); __threadfence(); st_release(prog + s, 1 << 30); }
+  }
+}
+
+template <int TB, int TR, int TC>
+constexpr size_t chase_tma_smem() {
+  return sizeof(cplx) * ((size_t)(TB | 1) * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * TB + 32) + 16;
+}
+
 __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restrict__ d, double* __restrict__ e, int n,
                                int LD, Mask mask) {
   const int b = blockIdx.y;
@@ -900,11 +1223,13 @@ int dw_band_chase(Handle* h, Mask mask) {
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
   static const bool no_fast = getenv("DWHMC_BAND_GENERIC") != nullptr;
   const bool fast = (bw == 100) && !no_fast;
-  const size_t fsmem = chase_fast_smem<100, 25, 20>();
+  static const bool use_tma = getenv("DWHMC_BAND_NOTMA") == nullptr;
+  const size_t fsmem = use_tma ? chase_tma_smem<100, 25, 20>() : chase_fast_smem<100, 25, 20>();
   if (fast) {
     static bool fattr[64] = {false};
     if (!fattr[h->device & 63]) {
       DW_CUDA(h, cudaFuncSetAttribute(chase_fast_kernel<100, 25, 20, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      DW_CUDA(h, cudaFuncSetAttribute(chase_tma_kernel<100, 25, 20, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       fattr[h->device & 63] = true;
     }
   }
@@ -918,7 +1243,8 @@ int dw_band_chase(Handle* h, Mask mask) {
     a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
     const int nch = std::min(per_launch, B - c0);
     void* args[] = {&a};
-    if (fast) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_fast_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
+    if (fast && use_tma) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_tma_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
+    else if (fast) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_fast_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
     else DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(nch * P), dim3(CT), args, smem, h->stream));
     h->launches++;
     if (a.clk) {
