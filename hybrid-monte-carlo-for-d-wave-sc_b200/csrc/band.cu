@@ -16,6 +16,7 @@
 // The numerics (LAPACK-style zlarfg / zhetd2 updates, application order of the blocks) are the
 // ones prototyped against LAPACK in tests/algo_proto_band.py.
 #include <cooperative_groups.h>
+#include <cuda.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include "dwhmc.h"
+#include "gemm_dmma.cuh"
 #include "internal.h"
 
 namespace {
@@ -730,24 +732,25 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int TB, int TR, int TC, int RB, int CB>
-__global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
+__global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmap) {
   static_assert(TR * RB == TB && TC * CB == TB && TR * TC <= CT && TB <= CT, "exact cover");
-  constexpr int LDB = TB | 1;
+  constexpr int LDB = TB;        // dense box layout of the tensor copies
+  constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
   constexpr int LD = 2 * TB;
   constexpr int NP = (TR > TC) ? TR : TC;
   const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
   if (!g.mask.on(chain)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_tma[];
   const int n = g.n;
-  cplx* Bc = reinterpret_cast<cplx*>(smem_raw);      // [TB][LDB]
+  cplx* Bc = reinterpret_cast<cplx*>(smem_tma);      // [TB][LDB]
   cplx* vs = Bc + LDB * TB;
   cplx* vp = vs + TB;
   cplx* us = vp + TB;
   cplx* xs = us + TB;
   cplx* tu = xs + TB;
   cplx* wc = tu + TB;
-  cplx* part = wc + TB;                              // [NP][TB]
-  cplx* red = part + NP * TB;                        // [32]
+  cplx* part = wc + TB;                              // [NP][LDP]
+  cplx* red = part + NP * LDP;                       // [32]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
   const int tid = threadIdx.x;
   const bool act = tid < TR * TC;
@@ -765,12 +768,16 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
   unsigned ephase = 0;                               // parity of the next-block barrier
   bool store_pending = false;
 
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
+#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
   for (int s = p; s < n - 1; s += g.P) {
     int k = 0, r0 = s + 1;
     cplx taup = zero;
     int lcar = 0;                                    // rows of the carried block in flight / in Bc
     while (true) {
       const int ln = min(TB, n - r0);
+      if (prof) tlast = clock64();
       if (k > 0) {
         // the carried block (issued at the end of the previous step) must have landed; u = Bn vp
         mbar_wait(bar, ephase);
@@ -787,17 +794,18 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
               if (ri + q * TR < lcar) cfma(acc[q], Bc[soff + cc * TC * LDB + q * TR], vj);
           }
 #pragma unroll
-          for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
+          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
         }
         __syncthreads();
         for (int i = tid; i < lcar; i += CT) {
           cplx u = part[i];
 #pragma unroll 5
-          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * TB + i]);
+          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * LDP + i]);
           us[i] = u;
         }
         __syncthreads();
       }
+      PH(0);
       if (k > 0 && ln <= 1) {
         for (int idx = tid; idx < ln * TB; idx += CT) {
           const int i = idx % ln, j = idx / ln;
@@ -815,6 +823,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         }
         __syncthreads();
       }
+      PH(1);
       // ---- prefetch the lower triangle of the diagonal block into registers
       cplx* baseD = AB + (size_t)r0 * LD + goff;
       cplx dreg[RB][CB];
@@ -839,6 +848,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
       // ---- B. reflector
       cplx tau; double beta;
       larfg_block(xs, vs, ln, red, tau, beta);
+      PH(2);
       for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
       if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
       cplx vr[RB];
@@ -856,7 +866,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
             cplx acc = zero;
 #pragma unroll
             for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
-            part[ri * TB + cj + cc * TC] = acc;
+            part[ri * LDP + cj + cc * TC] = acc;
           }
         }
         c = block_sum(c, red);
@@ -864,7 +874,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         for (int j = tid; j < TB; j += CT) {
           cplx z = part[j];
 #pragma unroll 5
-          for (int q = 1; q < TR; ++q) z = cadd(z, part[q * TB + j]);
+          for (int q = 1; q < TR; ++q) z = cadd(z, part[q * LDP + j]);
           cfms(z, c, cconj(vp[j]));
           wc[j] = cmul(ctau, z);
         }
@@ -892,13 +902,15 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         }
         fence_async();                                // generic-proxy writes of Bc -> visible to the bulk engine
         __syncthreads();
-        if (tid < TB) {
-          cplx* dst = AB + (size_t)(r0 - TB + tid) * LD + (TB - tid);
-          bulk_s2g(dst, Bc + tid * LDB, (unsigned)(ln * sizeof(cplx)));
+        if (tid == 0) {
+          // one tensor copy: rows r0 .. r0+TB-1 (rows >= n are clipped), columns r0-TB .. r0-1 of this chain
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                       ::"l"(&tmap), "r"(2 * r0), "r"(r0 - TB), "r"(chain), "r"(smem_u32(Bc)) : "memory");
           bulk_commit();
         }
         store_pending = true;
       }
+      PH(3);
       // ---- D. diagonal block from registers: x = tau D v, D Hermitian (lower part held)
       {
         // row part: sum_{j <= i} D[i,j] v[j]
@@ -918,13 +930,13 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
             }
           }
 #pragma unroll
-          for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
+          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
         }
         __syncthreads();
         for (int i = tid; i < ln; i += CT) {
           cplx wv = part[i];
 #pragma unroll 5
-          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * TB + i]);
+          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * LDP + i]);
           xs[i] = wv;
         }
         __syncthreads();
@@ -937,7 +949,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
 #pragma unroll
             for (int q = 0; q < RB; ++q)
               if (ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
-            part[ri * TB + j] = acc;
+            part[ri * LDP + j] = acc;
           }
         }
         __syncthreads();
@@ -945,7 +957,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         for (int i = tid; i < ln; i += CT) {
           cplx wv = xs[i];
 #pragma unroll 5
-          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * TB + i]);
+          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * LDP + i]);
           wv = cmul(tau, wv);
           xs[i] = wv;
           cfmac(dot, wv, vs[i]);
@@ -956,22 +968,23 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
         __syncthreads();
       }
+      PH(4);
       // ---- next block: fetch with the bulk engine while the diagonal block is updated and stored
       const int r1 = r0 + ln;
       const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
       if (store_pending) {
-        if (tid < TB) bulk_wait_read();               // the write-back has finished reading Bc
+        if (tid == 0) bulk_wait_read();               // the write-back has finished reading Bc
         __syncthreads();
       }
       if (l2 > 0) {
-        if (tid == 0) mbar_expect_tx(bar, (unsigned)(l2 * sizeof(cplx)) * TB);
-        __syncthreads();
-        if (tid < TB) {
+        if (tid == 0) {
           fence_async();
-          const cplx* src = AB + (size_t)(r0 + tid) * LD + (TB - tid);
-          bulk_g2s(Bc + tid * LDB, src, (unsigned)(l2 * sizeof(cplx)), bar);
+          mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));   // the full box counts, clipped rows are zero-filled
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       ::"r"(smem_u32(Bc)), "l"(&tmap), "r"(2 * r1), "r"(r0), "r"(chain), "r"(smem_u32(bar)) : "memory");
         }
       }
+      PH(5);
       // ---- D update and store (lower part, from registers)
       if (act) {
         cplx wr[RB];
@@ -996,7 +1009,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
         }
       }
       if (store_pending) {
-        if (tid < TB) bulk_wait_all();                // write-back performed in global memory
+        if (tid == 0) bulk_wait_all();                // write-back performed in global memory
         store_pending = false;
       }
       if (l2 == 0) break;
@@ -1004,18 +1017,47 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g) {
       taup = tau;
       lcar = l2;
       __syncthreads();
-      if (tid == 0) { fence_async(); __threadfence(); st_release(prog + s, k + 1); }
+      PH(6);
+      if (tid == 0) { fence_async(); st_release(prog + s, k + 1); }
+      PH(7);
       r0 = r1;
       ++k;
     }
     __syncthreads();
     if (tid == 0) { fence_async(); __threadfence(); st_release(prog + s, 1 << 30); }
   }
+  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
+#undef PH
 }
 
 template <int TB, int TR, int TC>
 constexpr size_t chase_tma_smem() {
-  return sizeof(cplx) * ((size_t)(TB | 1) * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * TB + 32) + 16;
+  return sizeof(cplx) * ((size_t)TB * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * (TB + 1) + 32) + 16;
+}
+
+// Tensor map of the band storage of all chains as the skewed view T[chain][c][r] = AB[chain][c LD + (r - c)]
+// = base + chain n LD + c (LD - 1) + r (in complex elements; FP64 element type, so the inner extent is 2 n).
+static int make_band_tensor_map(Handle* h, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    h->err = "cuTensorMapEncodeTiled not available";
+    return DWHMC_E_CUDA;
+  }
+  const cuuint64_t n = (cuuint64_t)h->n, LD = (cuuint64_t)h->band_LD, b = (cuuint64_t)h->band_b;
+  const cuuint64_t gdim[3] = {2 * n, n, (cuuint64_t)h->B};
+  const cuuint64_t gstr[2] = {(LD - 1) * sizeof(cplx), n * LD * sizeof(cplx)};
+  const cuuint32_t box[3] = {(cuuint32_t)(2 * b), (cuuint32_t)b, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult rc = reinterpret_cast<EncodeFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->A, gdim, gstr, box, estr,
+                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")"; return DWHMC_E_CUDA; }
+  return DWHMC_OK;
 }
 
 __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restrict__ d, double* __restrict__ e, int n,
@@ -1039,7 +1081,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
                                                            int nblk, Mask mask) {
   const int blk = blockIdx.x, ch = blockIdx.y;
   if (!mask.on(ch)) return;
-  __shared__ cplx Vs[32 * TG];           // row chunk [32][g]
+  __shared__ cplx Vs[32 * (TG + 1)];     // row chunk [32 rows][g columns], column index fastest
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* G = reinterpret_cast<cplx*>(smem_raw);          // [g][g] column-major
   cplx* T = G + g * g;                                   // [g][g+1] row-major rows
@@ -1061,7 +1103,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       const int r = idx & 31, c = idx >> 5;
       const int rr = rc + r;
       const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
-      Vs[c * 32 + r] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
+      Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
     }
     __syncthreads();
 #pragma unroll
@@ -1070,7 +1112,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       const int c1 = pidx % g, c2 = pidx / g;
       if (c2 < gg && c1 < gg) {
         cplx a = acc[q];
-        for (int r = 0; r < 32; ++r) cfmac(a, Vs[c1 * 32 + r], Vs[c2 * 32 + r]);
+        for (int r = 0; r < 32; ++r) cfmac(a, Vs[r * (TG + 1) + c1], Vs[r * (TG + 1) + c2]);
         acc[q] = a;
       }
     }
@@ -1103,6 +1145,179 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
   for (int idx = tid; idx < g * g; idx += 256) {
     const int r = idx % g, c = idx / g;
     out[c * TG + r] = T[r * (g + 1) + c];
+  }
+}
+
+// ---- fused staircase block reflector: Z[R, :] -= (Vb T) (Vb^H Z[R, :]) ---------------------------------
+// One CTA = (column part, block of the wavefront, chain).  Vb (<= 128 rows x <= 32 reflectors, zero outside the
+// staircase) and VT = Vb T stay in shared memory; the CTA walks its column tiles of 16 with cp.async double
+// buffering and runs two products per tile on the FP64 tensor cores (DMMA m8n8k4, four real DMMAs per complex
+// product):   W1 = Vb^H Zt (32 x 16, K = 128),   Zt - VT W1 (128 x 16, K = 32) written straight to global memory.
+// Blocks of one wavefront t = 2 (Gmax - G) + k touch disjoint rows and only depend on smaller t.
+constexpr int AR = 128, AG = 32, ANC = 16;
+constexpr int ALDV = 130, ALDT = 34, ALDZ = 132, ALDW = 36;
+constexpr int ATH = 512;             // 16 warps: four per scheduler keep the tensor pipe fed across barriers
+constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)2 * AG * ALDV + 2 * ANC * ALDZ + 2 * ANC * ALDW);
+static_assert(AG * ALDT <= 2 * ANC * ALDZ, "T is staged in the tile buffers");
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem, bool pred) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
+
+__global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Zall, const cplx* __restrict__ Vall,
+                                                            const cplx* __restrict__ Tall, const int* __restrict__ blk_s0,
+                                                            const int* __restrict__ blk_k, const int* __restrict__ wave_blk,
+                                                            const int* __restrict__ halfflag, int n, int b, int g, int nblk,
+                                                            int c_lo, int use_half, Mask mask) {
+  using dwg::dmma884;
+  const int chain = blockIdx.z;
+  if (!mask.on(chain)) return;
+  const int blk = wave_blk[blockIdx.y];
+  const int s0 = blk_s0[blk], k = blk_k[blk];
+  const int gg = min(g, n - 1 - s0);
+  const int rlo = s0 + 1 + k * b;
+  const int rows = min(n - rlo, b + gg - 1);
+  if (rows <= 0 || gg <= 0) return;
+  const int cstart = (use_half && halfflag[chain] != 0) ? c_lo : 0;
+  const int ntile = (n - cstart + ANC - 1) / ANC;
+  const int per = (ntile + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per, t1 = min(ntile, t0 + per);
+  if (t0 >= t1) return;
+  extern __shared__ __align__(16) unsigned char smem_apply[];
+  cplx* Vs = reinterpret_cast<cplx*>(smem_apply);   // [AG][ALDV]  Vs[m * ALDV + r] = Vb[r][m]
+  cplx* VTs = Vs + AG * ALDV;                         // [AG][ALDV]  (Vb T)[r][m]
+  cplx* Zs = VTs + AG * ALDV;                         // [2][ANC][ALDZ]
+  cplx* W1s = Zs + 2 * ANC * ALDZ;                    // [2 K halves][ANC][ALDW]
+  cplx* Ts = Zs;                                      // [AG][ALDT], prologue only
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const cplx zero = make_double2(0.0, 0.0);
+  const cplx* V = Vall + (size_t)chain * n * n;
+  cplx* Z = Zall + (size_t)chain * n * n;
+  const cplx* T = Tall + ((size_t)chain * nblk + blk) * TG * TG;
+  for (int idx = tid; idx < AG * AR; idx += ATH) {
+    const int r = idx % AR, m = idx / AR;
+    const bool ok = m < gg && r < rows && r - m >= 0 && r - m < b;
+    Vs[m * ALDV + r] = ok ? V[(size_t)(s0 + m) * n + rlo + r] : zero;
+  }
+  for (int idx = tid; idx < AG * AG; idx += ATH) {
+    const int r = idx % AG, c = idx / AG;
+    Ts[c * ALDT + r] = (r < gg && c < gg) ? T[c * TG + r] : zero;
+  }
+  __syncthreads();
+  // VT = Vb T  (128 x 32, K = 32): warp -> row tile, all four column tiles
+  {
+    const int mt = warp;
+    double cr[4][2], ci[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) cr[nt][0] = cr[nt][1] = ci[nt][0] = ci[nt][1] = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < AG; k0 += 4) {
+      const cplx a = Vs[(k0 + fk) * ALDV + mt * 8 + fr];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const cplx bb = Ts[(nt * 8 + fr) * ALDT + k0 + fk];
+        dmma884(cr[nt][0], cr[nt][1], a.x, bb.x);
+        dmma884(ci[nt][0], ci[nt][1], a.x, bb.y);
+        dmma884(cr[nt][0], cr[nt][1], -a.y, bb.y);
+        dmma884(ci[nt][0], ci[nt][1], a.y, bb.x);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) VTs[(nt * 8 + 2 * fk + e) * ALDV + mt * 8 + fr] = make_double2(cr[nt][e], ci[nt][e]);
+  }
+  __syncthreads();                                    // Ts (aliasing the tile buffers) is dead from here on
+  auto load_tile = [&](int t, int buf) {
+    cplx* dst = Zs + buf * ANC * ALDZ;
+    const int col0 = cstart + t * ANC;
+#pragma unroll
+    for (int it = 0; it < (ANC * AR) / ATH; ++it) {
+      const int idx = tid + it * ATH;
+      const int r = idx % AR, c = idx / AR;
+      const bool ok = r < rows && col0 + c < n;
+      cp16(dst + c * ALDZ + r, ok ? Z + (size_t)(col0 + c) * n + rlo + r : Z, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  load_tile(t0, 0);
+  const int kmax = (rows + 3) & ~3;                   // K range of the first product (rows beyond are zero)
+  const int khalf = min(kmax, ((kmax / 2 + 7) / 8) * 8);
+  for (int t = t0; t < t1; ++t) {
+    const int buf = (t - t0) & 1;
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();                                  // tile t landed; everyone is done with the other buffer
+    if (t + 1 < t1) load_tile(t + 1, buf ^ 1);
+    cplx* Zt = Zs + buf * ANC * ALDZ;
+    // ---- W1 = Vb^H Zt : warp -> (tile mt = w % 4, nt = (w / 4) % 2, K half w / 8); two accumulator sets over
+    //      alternating k-steps keep four independent DMMA chains in flight
+    {
+      const int mt = warp & 3, nt = (warp >> 2) & 1, kh = warp >> 3;
+      const int kb = kh ? khalf : 0, ke = kh ? kmax : khalf;
+      double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0, dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
+      const cplx* ap = Vs + (mt * 8 + fr) * ALDV + fk;
+      const cplx* bp = Zt + (nt * 8 + fr) * ALDZ + fk;
+      for (int k0 = kb; k0 < ke; k0 += 8) {
+        const cplx a = ap[k0], bb = bp[k0];
+        const bool two = k0 + 4 < ke;
+        const cplx a2 = two ? ap[k0 + 4] : zero, b2 = two ? bp[k0 + 4] : zero;
+        dmma884(cr0, cr1, a.x, bb.x);
+        dmma884(ci0, ci1, a.x, bb.y);
+        dmma884(dr0, dr1, a2.x, b2.x);
+        dmma884(di0, di1, a2.x, b2.y);
+        dmma884(cr0, cr1, a.y, bb.y);
+        dmma884(ci0, ci1, -a.y, bb.x);
+        dmma884(dr0, dr1, a2.y, b2.y);
+        dmma884(di0, di1, -a2.y, b2.x);
+      }
+      cplx* w = W1s + kh * ANC * ALDW;
+      w[(nt * 8 + 2 * fk) * ALDW + mt * 8 + fr] = make_double2(cr0 + dr0, ci0 + di0);
+      w[(nt * 8 + 2 * fk + 1) * ALDW + mt * 8 + fr] = make_double2(cr1 + dr1, ci1 + di1);
+    }
+    __syncthreads();
+    // ---- Zt - VT W1 -> global : warp -> row tile, both column tiles
+    if (warp * 8 < rows) {
+      double cr[2][2], ci[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const cplx c = Zt[(nt * 8 + 2 * fk + e) * ALDZ + warp * 8 + fr];
+          cr[nt][e] = c.x; ci[nt][e] = c.y;
+        }
+#pragma unroll
+      for (int k0 = 0; k0 < AG; k0 += 4) {
+        const cplx a = VTs[(k0 + fk) * ALDV + warp * 8 + fr];
+        cplx bb[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const cplx p0 = W1s[(nt * 8 + fr) * ALDW + k0 + fk], p1 = W1s[ANC * ALDW + (nt * 8 + fr) * ALDW + k0 + fk];
+          bb[nt] = make_double2(p0.x + p1.x, p0.y + p1.y);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          dmma884(cr[nt][0], cr[nt][1], -a.x, bb[nt].x);
+          dmma884(ci[nt][0], ci[nt][1], -a.x, bb[nt].y);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          dmma884(cr[nt][0], cr[nt][1], a.y, bb[nt].y);
+          dmma884(ci[nt][0], ci[nt][1], -a.y, bb[nt].x);
+        }
+      }
+      const int col0 = cstart + t * ANC;
+      const int r = warp * 8 + fr;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = col0 + nt * 8 + 2 * fk + e;
+          if (r < rows && c < n) Z[(size_t)c * n + rlo + r] = make_double2(cr[nt][e], ci[nt][e]);
+        }
+    }
   }
 }
 
@@ -1172,6 +1387,7 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
   // reflectors per block of the back-transformation: block height b + g - 1 a multiple of 64
   int g = 64 * ((bw + 16 + 63) / 64) - bw + 1;
   g = std::max(8, std::min(g, TG));
+  if (bw + 8 <= AR) g = std::min(AG, AR - bw + 1);      // fused block-reflector kernel: <= 32 reflectors, <= 128 rows
   h->band_g = g;
   // block list, application order: sweep groups last to first, steps ascending
   std::vector<int> bs0, bk;
@@ -1188,6 +1404,22 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
   }
   h->band_blk_s0 = bs0;
   h->band_blk_k = bk;
+  // wavefronts of mutually independent blocks: t = 2 (ngrp - 1 - G) + k (every dependency has a smaller t)
+  {
+    const int nb2 = (int)bs0.size();
+    std::vector<int> tval(nb2), order(nb2);
+    int tmax = 0;
+    for (int i = 0; i < nb2; ++i) {
+      tval[i] = 2 * (ngrp - 1 - bs0[i] / g) + bk[i];
+      order[i] = i;
+      tmax = std::max(tmax, tval[i]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return tval[a] < tval[c]; });
+    h->band_wave_blk = order;
+    h->band_wave_start.assign(tmax + 2, 0);
+    for (int i = 0; i < nb2; ++i) h->band_wave_start[tval[i] + 1]++;
+    for (int t = 0; t <= tmax; ++t) h->band_wave_start[t + 1] += h->band_wave_start[t];
+  }
   h->band_pos_host = pos;
   return DWHMC_OK;
 }
@@ -1243,7 +1475,15 @@ int dw_band_chase(Handle* h, Mask mask) {
     a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
     const int nch = std::min(per_launch, B - c0);
     void* args[] = {&a};
-    if (fast && use_tma) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_tma_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
+    if (fast && use_tma) {
+      static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
+      if (!h->band_tmap_set) {
+        DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap)));
+        h->band_tmap_set = true;
+      }
+      void* targs[] = {&a, h->band_tmap};
+      DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_tma_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), targs, fsmem, h->stream));
+    }
     else if (fast) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_fast_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
     else DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(nch * P), dim3(CT), args, smem, h->stream));
     h->launches++;
@@ -1251,7 +1491,7 @@ int dw_band_chase(Handle* h, Mask mask) {
       long long c[8];
       cudaStreamSynchronize(h->stream);
       cudaMemcpy(c, a.clk, sizeof(c), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "chase phases (Mclk): wait %.1f A+larfg %.1f C %.1f Dload %.1f Dcomp %.1f Eload %.1f Ecomp %.1f publish %.1f\n",
+      fprintf(stderr, "chase phase clocks (Mclk) [0..7]: %.1f %.1f %.1f %.1f %.1f %.1f %.1f %.1f\n",
               c[0] / 1e6, c[1] / 1e6, c[2] / 1e6, c[3] / 1e6, c[4] / 1e6, c[5] / 1e6, c[6] / 1e6, c[7] / 1e6);
     }
   }
@@ -1282,7 +1522,28 @@ int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
   if (half) { a.skip_flag = h->halfflag; a.skip_cols = h->N; }
   cplx* Z = h->A;
-  for (int blk = 0; blk < nblk; ++blk) {
+  static const bool no_fused = getenv("DWHMC_BAND_NOFUSE") != nullptr;
+  const bool fused = !no_fused && g <= AG && bw + g - 1 <= AR;
+  if (fused) {
+    static bool fattr[64] = {false};
+    if (!fattr[h->device & 63]) {
+      DW_CUDA(h, cudaFuncSetAttribute(band_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
+      fattr[h->device & 63] = true;
+    }
+    const int c_lo = half ? (h->N / 128) * 128 : 0;
+    const int nparts = 6;
+    const int nwave = (int)h->band_wave_start.size() - 1;
+    for (int t = 0; t < nwave; ++t) {
+      const int w0 = h->band_wave_start[t], nsub = h->band_wave_start[t + 1] - w0;
+      if (nsub <= 0) continue;
+      dim3 grid(nparts, nsub, B);
+      band_apply_kernel<<<grid, ATH, APPLY_SMEM, h->stream>>>(Z, h->V, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev,
+                                                               h->band_wave_dev + w0, h->halfflag, n, bw, g, nblk, c_lo,
+                                                               half ? 1 : 0, mask);
+      DW_LAUNCH_CHECK(h);
+    }
+  }
+  for (int blk = 0; blk < nblk && !fused; ++blk) {
     const int s0 = h->band_blk_s0[blk], k = h->band_blk_k[blk];
     const int gg = std::min(g, n - 1 - s0);
     const int rlo = s0 + 1 + k * bw;

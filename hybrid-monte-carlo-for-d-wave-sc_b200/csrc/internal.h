@@ -126,11 +126,15 @@ struct Handle {
   // band route (band.cu): half-bandwidth of the BdG matrix in the folded site order; 0 = dense route
   int band_b = 0, band_LD = 0, band_KT = 0, band_g = 0;
   std::vector<int> band_pos_host, band_blk_s0, band_blk_k;
+  std::vector<int> band_wave_blk, band_wave_start;   // blocks sorted into wavefronts of independent blocks
+  int* band_wave_dev = nullptr;
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase)
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
   cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
+  alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
+  bool band_tmap_set = false;
   // transport / spectra workspace (transport.cu), allocated on first use
   double* tr_work = nullptr; size_t tr_work_count = 0;
   double* tr_out = nullptr; size_t tr_out_count = 0;     // scal | sigma | dos | dosAN | ak | omega | dosgrid
