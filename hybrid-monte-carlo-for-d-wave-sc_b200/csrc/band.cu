@@ -1155,9 +1155,11 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
 // product):   W1 = Vb^H Zt (32 x 16, K = 128),   Zt - VT W1 (128 x 16, K = 32) written straight to global memory.
 // Blocks of one wavefront t = 2 (Gmax - G) + k touch disjoint rows and only depend on smaller t.
 constexpr int AR = 128, AG = 32, ANC = 16;
-constexpr int ALDV = 130, ALDT = 34, ALDZ = 132, ALDW = 36;
+// leading dimensions chosen per access pattern (16-byte elements, eight lanes per wavefront): operands read as
+// (row = lane / 4, k = lane % 4) need ld = 4 mod 8, operands read as (k = lane % 4, row = lane / 4) need ld = 2 mod 4
+constexpr int ALDV = 132, ALDVT = 130, ALDT = 34, ALDZ = 132, ALDW = 36;
 constexpr int ATH = 512;             // 16 warps: four per scheduler keep the tensor pipe fed across barriers
-constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)2 * AG * ALDV + 2 * ANC * ALDZ + 2 * ANC * ALDW);
+constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)AG * ALDV + AG * ALDVT + 2 * ANC * ALDZ + 2 * ANC * ALDW);
 static_assert(AG * ALDT <= 2 * ANC * ALDZ, "T is staged in the tile buffers");
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem, bool pred) {
@@ -1187,8 +1189,8 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
   if (t0 >= t1) return;
   extern __shared__ __align__(16) unsigned char smem_apply[];
   cplx* Vs = reinterpret_cast<cplx*>(smem_apply);   // [AG][ALDV]  Vs[m * ALDV + r] = Vb[r][m]
-  cplx* VTs = Vs + AG * ALDV;                         // [AG][ALDV]  (Vb T)[r][m]
-  cplx* Zs = VTs + AG * ALDV;                         // [2][ANC][ALDZ]
+  cplx* VTs = Vs + AG * ALDV;                         // [AG][ALDVT] (Vb T)[r][m]
+  cplx* Zs = VTs + AG * ALDVT;                         // [2][ANC][ALDZ]
   cplx* W1s = Zs + 2 * ANC * ALDZ;                    // [2 K halves][ANC][ALDW]
   cplx* Ts = Zs;                                      // [AG][ALDT], prologue only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1228,7 +1230,7 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) VTs[(nt * 8 + 2 * fk + e) * ALDV + mt * 8 + fr] = make_double2(cr[nt][e], ci[nt][e]);
+      for (int e = 0; e < 2; ++e) VTs[(nt * 8 + 2 * fk + e) * ALDVT + mt * 8 + fr] = make_double2(cr[nt][e], ci[nt][e]);
   }
   __syncthreads();                                    // Ts (aliasing the tile buffers) is dead from here on
   auto load_tile = [&](int t, int buf) {
@@ -1290,7 +1292,7 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
         }
 #pragma unroll
       for (int k0 = 0; k0 < AG; k0 += 4) {
-        const cplx a = VTs[(k0 + fk) * ALDV + warp * 8 + fr];
+        const cplx a = VTs[(k0 + fk) * ALDVT + warp * 8 + fr];
         cplx bb[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
@@ -1530,12 +1532,13 @@ int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
       DW_CUDA(h, cudaFuncSetAttribute(band_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
       fattr[h->device & 63] = true;
     }
-    const int c_lo = half ? (h->N / 128) * 128 : 0;
-    const int nparts = 6;
+    const int c_lo = half ? (h->N / ANC) * ANC : 0;        // 16-column tiles: no straddling columns to carry
     const int nwave = (int)h->band_wave_start.size() - 1;
     for (int t = 0; t < nwave; ++t) {
       const int w0 = h->band_wave_start[t], nsub = h->band_wave_start[t + 1] - w0;
       if (nsub <= 0) continue;
+      // column parts per block: enough CTAs for ~4 waves, as few as possible (each CTA rebuilds V T)
+      const int nparts = std::max(2, std::min(8, (4 * h->nsm + nsub * B - 1) / (nsub * B)));
       dim3 grid(nparts, nsub, B);
       band_apply_kernel<<<grid, ATH, APPLY_SMEM, h->stream>>>(Z, h->V, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev,
                                                                h->band_wave_dev + w0, h->halfflag, n, bw, g, nblk, c_lo,
@@ -1575,7 +1578,7 @@ int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   }
   {
     dim3 grid(n, B);
-    const int c_lo = half ? (h->N / 128) * 128 : 0;
+    const int c_lo = half ? (fused ? (h->N / ANC) * ANC : (h->N / 128) * 128) : 0;
     band_unpermute_kernel<<<grid, 256, 0, h->stream>>>(Z, U, h->band_pos, h->halfflag, c_lo, n, mask);
     DW_LAUNCH_CHECK(h);
   }
