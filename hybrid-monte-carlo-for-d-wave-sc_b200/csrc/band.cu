@@ -778,10 +778,24 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
     while (true) {
       const int ln = min(TB, n - r0);
       if (prof) tlast = clock64();
+      // Sweep s-1 must be two steps ahead (or finished).  The only element of this step's blocks that sweep s-1
+      // touches later than that is the bottom-right corner of the carried block (the first entry of the column its
+      // step k+1 annihilates): it is re-read here, after the wait, instead of being trusted from the early fetch.
+      if (s > 0) {
+        if (tid == 0) {
+          const int need = k + 2;
+          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
+        }
+        __syncthreads();
+      }
       if (k > 0) {
         // the carried block (issued at the end of the previous step) must have landed; u = Bn vp
         mbar_wait(bar, ephase);
         ephase ^= 1;
+        if (lcar == TB) {
+          if (tid == 0) Bc[(TB - 1) * LDB + TB - 1] = ldg2(AB + (size_t)(r0 - 1) * LD + TB);
+          __syncthreads();
+        }
         if (act) {
           cplx acc[RB];
 #pragma unroll
@@ -815,13 +829,6 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
         }
         for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
         break;
-      }
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = k + 3;
-          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
-        }
-        __syncthreads();
       }
       PH(1);
       // ---- prefetch the lower triangle of the diagonal block into registers
