@@ -425,285 +425,16 @@ __global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
 #undef PH
 }
 
-// ---- register-blocked chase kernel for a compile-time half-bandwidth -------------------------------
-// Same algorithm and data flow as chase_kernel; the b x b blocks are covered exactly by a TR x TC thread
-// grid with an RB x CB sub-block per thread (TR RB = TC CB = TB), so every global / shared offset is a
-// compile-time constant off one per-thread base and the matrix-vector products run on register operands.
-// All three block shapes share one address formula: element (i, j) of a block whose first column is c0 and
-// whose first row is c0 + o lies at AB + c0 LD + o + j (LD - 1) + i.
-template <int TB, int TR, int TC, int RB, int CB>
-__global__ void __launch_bounds__(CT, 1) chase_fast_kernel(ChaseArgs g) {
-  static_assert(TR * RB == TB && TC * CB == TB && TR * TC <= CT, "exact cover");
-  constexpr int LDB = TB | 1;
-  constexpr int LD = 2 * TB;
-  constexpr int NP = (TR > TC) ? TR : TC;
-  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
-  if (!g.mask.on(chain)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = g.n;
-  cplx* Bc = reinterpret_cast<cplx*>(smem_raw);      // [TB][LDB]
-  cplx* vs = Bc + LDB * TB;
-  cplx* vp = vs + TB;
-  cplx* us = vp + TB;
-  cplx* xs = us + TB;
-  cplx* tu = xs + TB;
-  cplx* wc = tu + TB;
-  cplx* part = wc + TB;                              // [NP][TB]
-  cplx* red = part + NP * TB;                        // [32]
-  const int tid = threadIdx.x;
-  const bool act = tid < TR * TC;
-  const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
-  const int soff = cj * LDB + ri;                    // + c TC LDB + q TR
-  const int goff = cj * (LD - 1) + ri;               // + c TC (LD - 1) + q TR
-  cplx* AB = g.AB + (size_t)chain * n * LD;
-  cplx* V = g.V + (size_t)chain * n * n;
-  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
-  int* prog = g.prog + (size_t)chain * n;
-  const cplx zero = make_double2(0.0, 0.0);
-
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
-#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
-  for (int s = p; s < n - 1; s += g.P) {
-    int k = 0, r0 = s + 1;
-    cplx taup = zero;
-    while (true) {
-      const int ln = min(TB, n - r0);
-      if (prof) tlast = clock64();
-      if (k > 0 && ln <= 1) {
-        for (int idx = tid; idx < ln * TB; idx += CT) {
-          const int i = idx % ln, j = idx / ln;
-          cplx a = Bc[j * LDB + i];
-          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
-          stg2(AB + (size_t)(r0 - TB + j) * LD + (TB + i - j), a);
-        }
-        for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
-        break;
-      }
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = k + 3;
-          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
-        }
-        __syncthreads();
-      }
-      PH(0);
-      // ---- prefetch the lower triangle of the diagonal block
-      cplx* baseD = AB + (size_t)r0 * LD + goff;
-      cplx dreg[RB][CB];
-#pragma unroll
-      for (int c = 0; c < CB; ++c)
-#pragma unroll
-        for (int q = 0; q < RB; ++q) {
-          const int i = ri + q * TR, j = cj + c * TC;
-          dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
-        }
-      // ---- A. column to annihilate
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
-      } else {
-        for (int i = tid; i < ln; i += CT) {
-          const cplx t = cmul(taup, us[i]);
-          tu[i] = t;
-          xs[i] = csub(Bc[i], t);
-        }
-      }
-      __syncthreads();
-      // ---- B. reflector
-      cplx tau; double beta;
-      larfg_block(xs, vs, ln, red, tau, beta);
-      PH(1);
-      for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
-      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
-      // this thread's rows of v (zero beyond ln, so partial blocks need no further predicates in the products)
-      cplx vr[RB];
-#pragma unroll
-      for (int q = 0; q < RB; ++q) vr[q] = (ri + q * TR < ln) ? vs[ri + q * TR] : zero;
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
-      } else {
-        // ---- C. carried block
-        cplx c = zero;
-        for (int i = tid; i < ln; i += CT) cfmac(c, vs[i], tu[i]);
-        if (act) {
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            cplx acc = zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
-            part[ri * TB + cj + cc * TC] = acc;
-          }
-        }
-        c = block_sum(c, red);
-        const cplx ctau = cconj(tau);
-        for (int j = tid; j < TB; j += CT) {
-          cplx z = part[j];
-#pragma unroll 5
-          for (int q = 1; q < TR; ++q) z = cadd(z, part[q * TB + j]);
-          cfms(z, c, cconj(vp[j]));
-          wc[j] = cmul(ctau, z);
-        }
-        __syncthreads();
-        if (act) {
-          cplx* baseC = AB + (size_t)(r0 - TB) * LD + TB + goff;
-          cplx tur[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) tur[q] = tu[min(ri + q * TR, TB - 1)];
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            const cplx cvp = cconj(vp[j]), wj = wc[j];
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              const int i = ri + q * TR;
-              cplx o = Bc[soff + cc * TC * LDB + q * TR];
-              cfms(o, tur[q], cvp);
-              cfms(o, vr[q], wj);
-              if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
-              if (i < ln) stg2(baseC + cc * TC * (LD - 1) + q * TR, o);
-            }
-          }
-        }
-        __syncthreads();
-      }
-      PH(2);
-      // ---- D. diagonal block: full Hermitian square into shared memory
-      if (act) {
-#pragma unroll
-        for (int cc = 0; cc < CB; ++cc)
-#pragma unroll
-          for (int q = 0; q < RB; ++q) {
-            const int i = ri + q * TR, j = cj + cc * TC;
-            if (i >= j && i < ln) {
-              cplx a = dreg[q][cc];
-              if (i == j) a.y = 0.0;
-              Bc[j * LDB + i] = a;
-              if (i != j) Bc[i * LDB + j] = cconj(a);
-            }
-          }
-      }
-      // ---- prefetch the next block
-      const int r1 = r0 + ln;
-      const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
-      cplx ereg[RB][CB];
-      {
-        cplx* baseE = AB + (size_t)r0 * LD + TB + goff;
-#pragma unroll
-        for (int cc = 0; cc < CB; ++cc)
-#pragma unroll
-          for (int q = 0; q < RB; ++q)
-            ereg[q][cc] = (act && ri + q * TR < l2) ? ldg2(baseE + cc * TC * (LD - 1) + q * TR) : zero;
-      }
-      __syncthreads();
-      PH(3);
-      {
-        // x = tau D v
-        if (act) {
-          cplx acc[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) acc[q] = zero;
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            const cplx vj = (j < ln) ? vs[j] : zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q) cfma(acc[q], Bc[soff + cc * TC * LDB + q * TR], vj);
-          }
-#pragma unroll
-          for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
-        }
-        __syncthreads();
-        cplx dot = zero;
-        for (int i = tid; i < ln; i += CT) {
-          cplx wv = part[i];
-#pragma unroll 5
-          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * TB + i]);
-          wv = cmul(tau, wv);
-          xs[i] = wv;
-          cfmac(dot, wv, vs[i]);
-        }
-        dot = block_sum(dot, red);
-        cplx alpha = cmul(tau, dot);
-        alpha.x *= -0.5; alpha.y *= -0.5;
-        for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
-        __syncthreads();
-        if (act) {
-          cplx wr[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) wr[q] = xs[min(ri + q * TR, TB - 1)];
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            const cplx cwj = cconj(xs[j]), cvj = cconj(vs[j]);
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              const int i = ri + q * TR;
-              if (i >= j && i < ln) {
-                cplx a = Bc[soff + cc * TC * LDB + q * TR];
-                cfms(a, vr[q], cwj);
-                cfms(a, wr[q], cvj);
-                if (i == j) a.y = 0.0;
-                stg2(baseD + cc * TC * (LD - 1) + q * TR, a);
-              }
-            }
-          }
-        }
-      }
-      // ---- E. next block
-      if (l2 == 0) break;
-      __syncthreads();
-      PH(4);
-      if (act) {
-        cplx acc[RB];
-#pragma unroll
-        for (int q = 0; q < RB; ++q) acc[q] = zero;
-#pragma unroll
-        for (int cc = 0; cc < CB; ++cc) {
-          const cplx vj = vs[cj + cc * TC];               // ln == TB here
-#pragma unroll
-          for (int q = 0; q < RB; ++q) {
-            Bc[soff + cc * TC * LDB + q * TR] = ereg[q][cc];
-            cfma(acc[q], ereg[q][cc], vj);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < RB; ++q) part[cj * TB + ri + q * TR] = acc[q];
-      }
-      __syncthreads();
-      for (int i = tid; i < l2; i += CT) {
-        cplx u = part[i];
-#pragma unroll 5
-        for (int q = 1; q < TC; ++q) u = cadd(u, part[q * TB + i]);
-        us[i] = u;
-      }
-      for (int i = tid; i < ln; i += CT) vp[i] = vs[i];
-      taup = tau;
-      __syncthreads();
-      PH(5);
-      if (tid == 0) { __threadfence(); st_release(prog + s, k + 1); }
-      PH(6);
-      r0 = r1;
-      ++k;
-    }
-    __syncthreads();
-    if (tid == 0) { __threadfence(); st_release(prog + s, 1 << 30); }
-  }
-  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
-#undef PH
-}
-
-template <int TB, int TR, int TC>
-constexpr size_t chase_fast_smem() {
-  return sizeof(cplx) * ((size_t)(TB | 1) * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * TB + 32);
-}
-
-// ---- TMA variant of the register-blocked chase kernel -------------------------------------------------
-// The two b x b block transfers of a step go through the bulk-copy engine instead of the load/store units:
-// the carried block is updated in place in shared memory and written back with one cp.async.bulk per column
-// (shared -> global, bulk group), the next block is fetched with one cp.async.bulk per column (global ->
-// shared, mbarrier complete_tx).  The store overlaps the diagonal-block products, the load overlaps the
-// diagonal-block update.  The diagonal block itself stays in registers (4 x 5 sub-block per thread); its
-// Hermitian product needs a row and a column reduction.
+// ---- TMA chase kernel for a compile-time half-bandwidth ----------------------------------------------------
+// Same algorithm and data flow as chase_kernel.  The b x b blocks are covered exactly by a TR x TC thread grid
+// with an RB x CB sub-block per thread (TR RB = TC CB = TB), so every offset is a compile-time constant off one
+// per-thread base and the products run on register operands.  The two b x b block transfers of a step go
+// through the TMA engine instead of the load/store units, as one tensor copy each over a 3-D tensor map of the
+// skewed band storage (rows beyond the matrix are clipped by the hardware, so partial blocks need no special
+// path): the carried block is updated in place in shared memory and written back (shared -> global, bulk
+// group), the next block is fetched (global -> shared, mbarrier complete_tx).  The store overlaps the
+// diagonal-block products, the load overlaps the diagonal-block update.  The diagonal block itself stays in
+// registers; its Hermitian product needs a row and a column reduction.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -717,14 +448,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -877,6 +600,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
           }
         }
         c = block_sum(c, red);
+        PH(1);
         const cplx ctau = cconj(tau);
         for (int j = tid; j < TB; j += CT) {
           cplx z = part[j];
@@ -1344,6 +1068,8 @@ __global__ void __launch_bounds__(256) band_unpermute_kernel(const cplx* __restr
 
 }  // namespace
 
+bool dw_band_has_tma_kernel(int bw);
+
 // ring fold: positions 0, L-1, 1, L-2, ... -> consecutive indices
 static std::vector<int> fold_positions(int L) {
   std::vector<int> pos(L);
@@ -1383,9 +1109,10 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
     }
   }
   bw = std::max(bw, 2);
-  // Opt-in (DWHMC_BAND=1): correct and parity-tested, but at L = 24 the bulge chase (95 ms per 64 chains)
-  // is still slower than the dense tridiagonalisation (83 ms); see DESIGN.md section 3.
-  int want = 0;
+  // Default wherever a compile-time TMA chase kernel exists for this bandwidth (faster than the dense route at
+  // every size measured, 12 <= L <= 24); DWHMC_BAND=0 forces the dense route, DWHMC_BAND=1 the band route (with
+  // the generic chase kernel if need be).
+  int want = dw_band_has_tma_kernel(bw) ? 1 : 0;
   if (const char* e = getenv("DWHMC_BAND")) want = atoi(e);
   const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
   // the chase kernel keeps 20 block elements per thread in registers: b^2 <= 20 * 512
@@ -1442,38 +1169,17 @@ int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx*
   return DWHMC_OK;
 }
 
-// h->A (band) -> h->d, h->e, h->V (reflectors, column s = sweep s), h->band_tau
-int dw_band_chase(Handle* h, Mask mask) {
+// launch helper: P persistent CTAs per chain, all co-resident (cooperative launch), chains in slices if needed
+template <class Launch>
+static int chase_launch_loop(Handle* h, Mask mask, const void* kern, size_t smem, Launch launch) {
   const int n = h->n, B = h->B, bw = h->band_b;
-  const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
-  static bool attr_set[64] = {false};
-  if (!attr_set[h->device & 63]) {
-    DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set[h->device & 63] = true;
-  }
-  int nsm = 0;
-  DW_CUDA(h, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
   int per_sm = 0;
-  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chase_kernel, CT, smem));
-  const int cap = nsm * per_sm;
+  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT, smem));
+  const int cap = h->nsm * per_sm;
   if (cap < 1) { h->err = "dw_band_chase: kernel does not fit"; return DWHMC_E_CUDA; }
   int P = std::max(1, std::min(4, cap / B));
   if (const char* e = getenv("DWHMC_BAND_P")) P = std::max(1, std::min(atoi(e), cap));
   const int per_launch = std::max(1, cap / P);                    // chains per launch
-  DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * (size_t)n * B, h->stream));
-  DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
-  static const bool no_fast = getenv("DWHMC_BAND_GENERIC") != nullptr;
-  const bool fast = (bw == 100) && !no_fast;
-  static const bool use_tma = getenv("DWHMC_BAND_NOTMA") == nullptr;
-  const size_t fsmem = use_tma ? chase_tma_smem<100, 25, 20>() : chase_fast_smem<100, 25, 20>();
-  if (fast) {
-    static bool fattr[64] = {false};
-    if (!fattr[h->device & 63]) {
-      DW_CUDA(h, cudaFuncSetAttribute(chase_fast_kernel<100, 25, 20, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      DW_CUDA(h, cudaFuncSetAttribute(chase_tma_kernel<100, 25, 20, 4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      fattr[h->device & 63] = true;
-    }
-  }
   for (int c0 = 0; c0 < B; c0 += per_launch) {
     ChaseArgs a;
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
@@ -1483,18 +1189,7 @@ int dw_band_chase(Handle* h, Mask mask) {
     if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
     a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
     const int nch = std::min(per_launch, B - c0);
-    void* args[] = {&a};
-    if (fast && use_tma) {
-      static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
-      if (!h->band_tmap_set) {
-        DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap)));
-        h->band_tmap_set = true;
-      }
-      void* targs[] = {&a, h->band_tmap};
-      DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_tma_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), targs, fsmem, h->stream));
-    }
-    else if (fast) DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_fast_kernel<100, 25, 20, 4, 5>, dim3(nch * P), dim3(CT), args, fsmem, h->stream));
-    else DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(nch * P), dim3(CT), args, smem, h->stream));
+    DW_TRY(launch(a, nch * P));
     h->launches++;
     if (a.clk) {
       long long c[8];
@@ -1503,6 +1198,62 @@ int dw_band_chase(Handle* h, Mask mask) {
       fprintf(stderr, "chase phase clocks (Mclk) [0..7]: %.1f %.1f %.1f %.1f %.1f %.1f %.1f %.1f\n",
               c[0] / 1e6, c[1] / 1e6, c[2] / 1e6, c[3] / 1e6, c[4] / 1e6, c[5] / 1e6, c[6] / 1e6, c[7] / 1e6);
     }
+  }
+  return DWHMC_OK;
+}
+
+template <int TB, int TR, int TC, int RB, int CB>
+static int chase_tma_dispatch(Handle* h, Mask mask) {
+  auto kern = chase_tma_kernel<TB, TR, TC, RB, CB>;
+  const size_t smem = chase_tma_smem<TB, TR, TC>();
+  static bool attr[64] = {false};
+  if (!attr[h->device & 63]) {
+    DW_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[h->device & 63] = true;
+  }
+  static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
+  if (!h->band_tmap_set) {
+    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap)));
+    h->band_tmap_set = true;
+  }
+  return chase_launch_loop(h, mask, (const void*)kern, smem, [&](ChaseArgs& a, int ctas) -> int {
+    void* targs[] = {&a, h->band_tmap};
+    DW_CUDA(h, cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(CT), targs, smem, h->stream));
+    return DWHMC_OK;
+  });
+}
+
+// half-bandwidths with a compile-time TMA kernel: b = 4 L + 4 for the short side L = 6, 8, ..., 20, 24
+// (92 = 4 x 23 has no exact TR x TC cover within 512 threads)
+bool dw_band_has_tma_kernel(int bw) { return bw >= 28 && bw <= 100 && (bw - 28) % 8 == 0 && bw != 92; }
+
+// h->A (band) -> h->d, h->e, h->V (reflectors, column s = sweep s), h->band_tau
+int dw_band_chase(Handle* h, Mask mask) {
+  const int n = h->n, B = h->B, bw = h->band_b;
+  DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * (size_t)n * B, h->stream));
+  DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
+  static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
+  if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 20, 4, 5>(h, mask)));
+  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
+  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
+  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));
+  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<60, 15, 20, 4, 3>(h, mask)));
+  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<52, 13, 26, 4, 2>(h, mask)));
+  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<44, 22, 22, 2, 2>(h, mask)));
+  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<36, 18, 18, 2, 2>(h, mask)));
+  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<28, 14, 14, 2, 2>(h, mask)));
+  else {
+    const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
+    static bool attr_set[64] = {false};
+    if (!attr_set[h->device & 63]) {
+      DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      attr_set[h->device & 63] = true;
+    }
+    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, smem, [&](ChaseArgs& a, int ctas) -> int {
+      void* args[] = {&a};
+      DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctas), dim3(CT), args, smem, h->stream));
+      return DWHMC_OK;
+    }));
   }
   dim3 grid((n + 255) / 256, B);
   band_de_kernel<<<grid, 256, 0, h->stream>>>(h->A, h->d, h->e, n, h->band_LD, mask);
