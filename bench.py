@@ -33,6 +33,8 @@ METRIC = "HMC trajectories/sec at L=24 (disordered T-scan shard, Nt=6)"
 # one ncu --set full capture of the dominant kernel (first hemv launch of a solve, 64 chains, n=1152):
 # dram__bytes_read.sum + dram__bytes_write.sum vs the algorithmic bytes of that launch (profiles/r01e_*)
 NCU_HEMV = {"dram_bytes": 691.7e6, "algorithmic_bytes": 678.9e6}
+# one ncu --set full capture of the bulge-chase kernel (64 chains, n = 1152, b = 100): DRAM read + write per launch
+NCU_CHASE = {"dram_bytes": 34.24e9 + 52.09e9}
 
 
 def temperatures(n_points=32):
@@ -271,16 +273,55 @@ def run_ours(args):
     cb.set_profiling(1); cb.reset_timers()
     cb.run_sweeps(1, Nt, dt)
     tm = cb.timers()
-    cb.set_profiling(2); cb.reset_timers()          # per-launch hemv timing (groups serialised)
-    cb.run_sweeps(1, Nt, dt)
-    tm["hemv_ms"] = cb.timers()["hemv_ms"]
+    if not cb.band_halfwidth():
+        cb.set_profiling(2); cb.reset_timers()      # dense route: per-launch hemv timing (groups serialised)
+        cb.run_sweeps(1, Nt, dt)
+        tm["hemv_ms"] = cb.timers()["hemv_ms"]
     cb.set_profiling(0)
     eig_ms = tm["tridiagonalize_ms"] + tm["stedc_ms"] + tm["backtransform_ms"]
     n_solves = tm["eigensolves"]                       # batched solves (each = B matrices)
     flops_per_solve = B * (40.0 / 3.0) * n ** 3        # 40/3 n^3 per eigendecomposition
     eig_tflops = n_solves * flops_per_solve / (eig_ms * 1e-3) / 1e12
-    hemv_bytes = B * 8.0 * sum((n - j - 1) * (n - j) for j in range(n - 1))   # lower triangle incl. diagonal, 16 B each
-    hemv_gbs = n_solves * hemv_bytes / (tm["hemv_ms"] * 1e-3) / 1e9
+    bw = cb.band_halfwidth()
+    if bw:
+        # band route: the dominant kernel is the bulge chase, one launch per batched solve.  Algorithmic bytes =
+        # what a step must move between global memory and the SM: carried block out (rows x b), next block in
+        # (rows' x b), diagonal block in and out (lower triangle), 16 B per element, summed over all sweeps / steps.
+        per_chain = 0
+        for s_ in range(n - 1):
+            r0, k_ = s_ + 1, 0
+            while r0 < n:
+                ln = min(bw, n - r0)
+                if k_ > 0 and ln <= 1:
+                    per_chain += ln * bw
+                    break
+                if k_ > 0:
+                    per_chain += ln * bw                 # carried block written back
+                per_chain += ln * (ln + 1)               # diagonal block, lower triangle, read + write
+                r1 = r0 + ln
+                if r1 >= n:
+                    break
+                per_chain += min(bw, n - r1) * ln        # next block read
+                r0, k_ = r1, k_ + 1
+        dom_bytes = B * 16.0 * per_chain
+        dom_ms = tm["tridiagonalize_ms"]
+        dom_gbs = n_solves * dom_bytes / (dom_ms * 1e-3) / 1e9
+        dom = {"kernel": "chase_tma_kernel (band -> tridiagonal bulge chase; one cooperative launch per batched eigensolve, "
+                         "128 persistent CTAs)",
+               "traffic": NCU_CHASE["dram_bytes"],
+               "traffic_note": "ncu --set full (profiles/r01g_chase_tma_full.ncu-rep): dram read 34.2 GB + write 52.1 GB per launch; "
+                               "below the algorithmic count because consecutive sweeps re-read each other's blocks from L2 (73 % hit)",
+               "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": dom_ms * 1e3 / n_solves,
+               "share_of_eigensolve": dom_ms / eig_ms}
+    else:
+        dom_bytes = B * 8.0 * sum((n - j - 1) * (n - j) for j in range(n - 1))   # lower triangle incl. diagonal, 16 B each
+        dom_gbs = n_solves * dom_bytes / (tm["hemv_ms"] * 1e-3) / 1e9
+        dom = {"kernel": "hemv_reg_kernel (y = A[j+1:, j+1:] v, lower triangle; 1151 column steps per batched eigensolve)",
+               "traffic": NCU_HEMV["dram_bytes"] / NCU_HEMV["algorithmic_bytes"] * dom_bytes / (n - 1),
+               "traffic_note": "ncu --set full, first launch of a solve (profiles/r01e_hemv_reg_full.ncu-rep), scaled to the average launch",
+               "algorithmic_bytes_per_launch": dom_bytes / (n - 1),
+               "avg_launch_us": tm["hemv_ms"] * 1e3 / (n_solves * (n - 1)),
+               "share_of_eigensolve_if_serial": tm["hemv_ms"] / eig_ms}
 
     # ---- end-of-run gather of the observables table (the only collective of the run)
     table = gather_table(np.concatenate([dHs[:, None], acc[:, None].astype(float), obs], axis=1), ids, n_chains,
@@ -305,21 +346,15 @@ def run_ours(args):
                     "api": "ChainBatch.hmc_sweep(pi0, uniforms from pinned host) + measure_observables -> host"},
             "gpu_launches": launches,
             "clocks": clk.summary(),
-            # dominant kernel of the step: the trailing-matrix product of the tridiagonalisation (HBM-bound)
-            "roofline": {"bound": "hbm", "kernel": "hemv_reg_kernel (y = A[j+1:, j+1:] v, lower triangle; 1151 launches per batched eigensolve)",
-                         "achieved": hemv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hemv_gbs / hbm_peak,
-                         "traffic": NCU_HEMV["dram_bytes"] / NCU_HEMV["algorithmic_bytes"] * hemv_bytes / (n - 1),
-                         "traffic_note": "ncu --set full, first launch of a solve (profiles/r01e_hemv_reg_full.ncu-rep): "
-                                         f"dram read+write {NCU_HEMV['dram_bytes']:.3e} B for {NCU_HEMV['algorithmic_bytes']:.3e} "
-                                         "algorithmic B; scaled here to the average launch",
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes_per_launch": hemv_bytes / (n - 1),
-                         "avg_launch_us": tm["hemv_ms"] * 1e3 / (n_solves * (n - 1) * 2),
-                         "launch_note": "two launches per column (chain groups of 32); bytes = 16 B x lower triangle incl. diagonal x 64 chains",
-                         "share_of_eigensolve_if_serial": tm["hemv_ms"] / eig_ms},
+            # dominant kernel of the step (memory-side roofline)
+            "roofline": dict({"bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dom_gbs / hbm_peak,
+                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+                             **dom),
             # the north star's FP64 tensor target is stated on the whole dense eigensolve
-            "roofline_tensor": {"bound": "tensor", "kernel": "batched Hermitian eigensolve (hetrd + stedc + back-transform); "
-                                                             "DMMA kernels: zgemm_dmma_kernel, dc_gemm2_kernel",
+            "roofline_tensor": {"bound": "tensor", "kernel": "batched Hermitian eigensolve (band route: chase + D&C + fused staircase back-transformation; DMMA "
+                                          "kernels: band_apply_kernel, dc_gemm2_kernel)" if bw else
+                                          "batched Hermitian eigensolve (hetrd + stedc + back-transform); DMMA kernels: zgemm_dmma_kernel, dc_gemm2_kernel",
+                                "route": "band" if bw else "dense", "half_bandwidth": bw,
                                 "achieved": eig_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eig_tflops / fp64_peak,
                                 "traffic": None,
                                 "peak_source": "measured live: torch.matmul fp64 4096^3 (cuBLAS DGEMM); MEASURED_PEAKS.json "

@@ -235,6 +235,13 @@ int dwhmc_destroy(dwhmc_handle hh) {
   return DWHMC_OK;
 }
 
+int dwhmc_eigensolver_route(dwhmc_handle hh, int* half_bandwidth) {
+  H_ENTER(hh);
+  if (!half_bandwidth) BADARG("dwhmc_eigensolver_route: NULL");
+  *half_bandwidth = h->band_b;
+  return DWHMC_OK;
+}
+
 int dwhmc_dims(dwhmc_handle hh, int* B, int* N, int* n) {
   H_ENTER(hh);
   if (B) *B = h->B;

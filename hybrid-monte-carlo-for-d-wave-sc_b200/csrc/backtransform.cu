@@ -169,8 +169,16 @@ int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
   };
   const bool band = ph && h->band_b > 0;
   tic();
-  if (band) DW_TRY(dw_band_chase(h, mask));
-  else DW_TRY(dw_hetrd(h, U_out, mask));
+  if (band) {
+    DW_TRY(dw_band_chase(h, mask));
+    // the T factors of the back-transformation only need the reflectors: compute them beside the D&C stage
+    DW_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    DW_CUDA(h, cudaStreamWaitEvent(h->gstream[0], h->ev_fork, 0));
+    DW_TRY(dw_band_tfactors(h, mask, h->gstream[0]));
+    DW_CUDA(h, cudaEventRecord(h->ev_join[0], h->gstream[0]));
+  } else {
+    DW_TRY(dw_hetrd(h, U_out, mask));
+  }
   toc(1);
   tic();
   DW_TRY(dw_stedc(h, mask));
@@ -178,7 +186,10 @@ int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
   DW_TRY(dw_stedc_output(h, E_out, band ? h->A : U_out, mask, ph));
   toc(2);
   tic();
-  if (band) DW_TRY(dw_band_backtransform(h, U_out, mask, ph));
+  if (band) {
+    DW_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[0], 0));
+    DW_TRY(dw_band_backtransform(h, U_out, mask, ph));
+  }
   else DW_TRY(dw_backtransform(h, U_out, mask, ph));
   if (ph && h->ph_mode) DW_TRY(dw_ph_mirror(h, E_out, U_out, mask));
   toc(3);

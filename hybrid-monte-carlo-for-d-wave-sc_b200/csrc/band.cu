@@ -1262,21 +1262,26 @@ int dw_band_chase(Handle* h, Mask mask) {
 }
 
 // Zb (n x n complex, band row order, in h->A) <- Q2 Zb, then rows back to site order into U
+// T factors of all staircase blocks (needs only the chase output, so it can run beside the D&C stage)
+int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream) {
+  const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
+  const int nblk = (int)h->band_blk_s0.size();
+  const size_t smem = sizeof(cplx) * ((size_t)g * g + (size_t)g * (g + 1));
+  static bool attr_set[64] = {false};
+  if (!attr_set[h->device & 63]) {
+    DW_CUDA(h, cudaFuncSetAttribute(band_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set[h->device & 63] = true;
+  }
+  dim3 grid(nblk, B);
+  band_tfactor_kernel<<<grid, 256, smem, stream>>>(h->V, h->band_tau, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev, n, bw,
+                                                   g, h->band_KT, nblk, mask);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
 int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
   const int nblk = (int)h->band_blk_s0.size();
-  {
-    const size_t smem = sizeof(cplx) * ((size_t)g * g + (size_t)g * (g + 1));
-    static bool attr_set[64] = {false};
-    if (!attr_set[h->device & 63]) {
-      DW_CUDA(h, cudaFuncSetAttribute(band_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set[h->device & 63] = true;
-    }
-    dim3 grid(nblk, B);
-    band_tfactor_kernel<<<grid, 256, smem, h->stream>>>(h->V, h->band_tau, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev,
-                                                        n, bw, g, h->band_KT, nblk, mask);
-    DW_LAUNCH_CHECK(h);
-  }
   const bool half = ph && h->ph_mode;
   ZgemmArgs a;
   a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;

@@ -199,6 +199,7 @@ int dw_assemble_for_solve(Handle* h, const double* w, const double* par3, const 
 int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>& nnn);
 int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx* delta, Mask mask);
 int dw_band_chase(Handle* h, Mask mask);
+int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream);
 int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
 
 // generic batched complex GEMM on FP64 tensor cores (gemm_dmma.cu)

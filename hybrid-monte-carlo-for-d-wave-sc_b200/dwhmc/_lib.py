@@ -65,6 +65,7 @@ PROTOTYPES = {
     "dwhmc_commit": [_vp, _ip],
     "dwhmc_hmc_sweep": [_vp, _ip, _dp, _dp, _dp, _ip, _dp],
     "dwhmc_run_sweeps": [_vp, _i, _ip, _dp, _ip, _dp, _dp],
+    "dwhmc_eigensolver_route": [_vp, C.POINTER(C.c_int)],
     "dwhmc_init_state": [_vp, _dp, _dp],
     "dwhmc_get_disorder": [_vp, _dp],
     "dwhmc_measure_transport": [_vp, C.c_double, _dp, _i, _dp, _i, _dp, _dp, _dp, _dp, _dp],

@@ -236,6 +236,12 @@ class ChainBatch:
         check(lib.dwhmc_run_sweeps(self._h, n_sweeps, iptr(nt), dptr(dtv), iptr(nacc), dptr(dH), dptr(obs)), self._h)
         return nacc, dH, obs
 
+    def band_halfwidth(self) -> int:
+        """0 = dense eigensolver route; otherwise the half-bandwidth the band route works with."""
+        out = C.c_int(0)
+        check(lib.dwhmc_eigensolver_route(self._h, C.byref(out)), self._h)
+        return int(out.value)
+
     # ---- instrumentation
     def set_profiling(self, level):
         """0 off; 1 per-stage CUDA-event timers; 2 also times every hemv launch (serialises the chain groups)."""

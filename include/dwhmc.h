@@ -56,6 +56,10 @@ enum {
 int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly,
                  const int64_t* nn_table, const int64_t* nnn_table);
 int dwhmc_destroy(dwhmc_handle h);
+/* which eigensolver route this handle uses: *half_bandwidth = 0 for the dense route (blocked
+ * tridiagonalisation), else the half-bandwidth of the BdG matrix in the folded site order (band route:
+ * bulge chase + staircase block reflectors).  Same results either way; instrumentation only. */
+int dwhmc_eigensolver_route(dwhmc_handle h, int* half_bandwidth);
 /* last error text of this handle (or of the failed create when h == NULL) */
 const char* dwhmc_last_error(dwhmc_handle h);
 /* library / build information string */
