@@ -172,6 +172,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     const size_t nblk = h->band_blk_s0.size();
     AL(h->band_pos, (size_t)n); AL(h->band_prog, nB); AL(h->band_tau, nB * h->band_KT);
     AL(h->band_T, nblk * 64 * 64 * B);
+    if (h->band_g <= 32 && h->band_b + h->band_g - 1 <= 128) AL(h->band_VT, nblk * 32 * 128 * B);
     AL(h->band_blk_s0_dev, nblk); AL(h->band_blk_k_dev, nblk); AL(h->band_wave_dev, nblk);
     if ((rc = h2d(h, h->band_wave_dev, h->band_wave_blk.data(), sizeof(int) * nblk)) != DWHMC_OK) return fail(rc);
     if ((rc = h2d(h, h->band_pos, h->band_pos_host.data(), sizeof(int) * n)) != DWHMC_OK) return fail(rc);

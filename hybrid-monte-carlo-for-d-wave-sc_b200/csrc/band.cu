@@ -807,9 +807,9 @@ __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restric
 // [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block.
 constexpr int TG = 64;               // max reflectors per block
 __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restrict__ Vall, const cplx* __restrict__ tau2,
-                                                           cplx* __restrict__ Tall, const int* __restrict__ blk_s0,
-                                                           const int* __restrict__ blk_k, int n, int b, int g, int KT,
-                                                           int nblk, Mask mask) {
+                                                           cplx* __restrict__ Tall, cplx* __restrict__ VTall,
+                                                           const int* __restrict__ blk_s0, const int* __restrict__ blk_k,
+                                                           int n, int b, int g, int KT, int nblk, Mask mask) {
   const int blk = blockIdx.x, ch = blockIdx.y;
   if (!mask.on(ch)) return;
   __shared__ cplx Vs[32 * (TG + 1)];     // row chunk [32 rows][g columns], column index fastest
@@ -877,11 +877,32 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
     const int r = idx % g, c = idx / g;
     out[c * TG + r] = T[r * (g + 1) + c];
   }
+  // VT = Vb T for the fused back-transformation kernel: [32 columns][128 rows] per block, zero padded
+  if (VTall != nullptr) {
+    cplx* vt = VTall + ((size_t)ch * nblk + blk) * (32 * 128);
+    for (int rc = 0; rc < 128; rc += 32) {
+      __syncthreads();
+      for (int idx = tid; idx < 32 * gg; idx += 256) {
+        const int r = idx & 31, c = idx >> 5;
+        const int rr = rc + r;
+        const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
+        Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < 32 * 32; idx += 256) {
+        const int r = idx & 31, m = idx >> 5;
+        cplx a = zero;
+        if (m < gg && rc + r < rows)
+          for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
+        vt[m * 128 + rc + r] = a;
+      }
+    }
+  }
 }
 
 // ---- fused staircase block reflector: Z[R, :] -= (Vb T) (Vb^H Z[R, :]) ---------------------------------
 // One CTA = (column part, block of the wavefront, chain).  Vb (<= 128 rows x <= 32 reflectors, zero outside the
-// staircase) and VT = Vb T stay in shared memory; the CTA walks its column tiles of 16 with cp.async double
+// staircase) and VT = Vb T (from band_tfactor_kernel) stay in shared memory; the CTA walks its column tiles of 16 with cp.async double
 // buffering and runs two products per tile on the FP64 tensor cores (DMMA m8n8k4, four real DMMAs per complex
 // product):   W1 = Vb^H Zt (32 x 16, K = 128),   Zt - VT W1 (128 x 16, K = 32) written straight to global memory.
 // Blocks of one wavefront t = 2 (Gmax - G) + k touch disjoint rows and only depend on smaller t.
@@ -891,7 +912,6 @@ constexpr int AR = 128, AG = 32, ANC = 16;
 constexpr int ALDV = 132, ALDVT = 130, ALDT = 34, ALDZ = 132, ALDW = 36;
 constexpr int ATH = 512;             // 16 warps: four per scheduler keep the tensor pipe fed across barriers
 constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)AG * ALDV + AG * ALDVT + 2 * ANC * ALDZ + 2 * ANC * ALDW);
-static_assert(AG * ALDT <= 2 * ANC * ALDZ, "T is staged in the tile buffers");
 
 __device__ __forceinline__ void cp16(void* smem, const void* gmem, bool pred) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -900,7 +920,7 @@ __device__ __forceinline__ void cp16(void* smem, const void* gmem, bool pred) {
 }
 
 __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Zall, const cplx* __restrict__ Vall,
-                                                            const cplx* __restrict__ Tall, const int* __restrict__ blk_s0,
+                                                            const cplx* __restrict__ VTall, const int* __restrict__ blk_s0,
                                                             const int* __restrict__ blk_k, const int* __restrict__ wave_blk,
                                                             const int* __restrict__ halfflag, int n, int b, int g, int nblk,
                                                             int c_lo, int use_half, Mask mask) {
@@ -923,47 +943,19 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
   cplx* VTs = Vs + AG * ALDV;                         // [AG][ALDVT] (Vb T)[r][m]
   cplx* Zs = VTs + AG * ALDVT;                         // [2][ANC][ALDZ]
   cplx* W1s = Zs + 2 * ANC * ALDZ;                    // [2 K halves][ANC][ALDW]
-  cplx* Ts = Zs;                                      // [AG][ALDT], prologue only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const cplx zero = make_double2(0.0, 0.0);
   const cplx* V = Vall + (size_t)chain * n * n;
   cplx* Z = Zall + (size_t)chain * n * n;
-  const cplx* T = Tall + ((size_t)chain * nblk + blk) * TG * TG;
+  const cplx* VT = VTall + ((size_t)chain * nblk + blk) * (AG * AR);
   for (int idx = tid; idx < AG * AR; idx += ATH) {
     const int r = idx % AR, m = idx / AR;
     const bool ok = m < gg && r < rows && r - m >= 0 && r - m < b;
     Vs[m * ALDV + r] = ok ? V[(size_t)(s0 + m) * n + rlo + r] : zero;
-  }
-  for (int idx = tid; idx < AG * AG; idx += ATH) {
-    const int r = idx % AG, c = idx / AG;
-    Ts[c * ALDT + r] = (r < gg && c < gg) ? T[c * TG + r] : zero;
+    VTs[m * ALDVT + r] = VT[idx];
   }
   __syncthreads();
-  // VT = Vb T  (128 x 32, K = 32): warp -> row tile, all four column tiles
-  {
-    const int mt = warp;
-    double cr[4][2], ci[4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) cr[nt][0] = cr[nt][1] = ci[nt][0] = ci[nt][1] = 0.0;
-#pragma unroll
-    for (int k0 = 0; k0 < AG; k0 += 4) {
-      const cplx a = Vs[(k0 + fk) * ALDV + mt * 8 + fr];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const cplx bb = Ts[(nt * 8 + fr) * ALDT + k0 + fk];
-        dmma884(cr[nt][0], cr[nt][1], a.x, bb.x);
-        dmma884(ci[nt][0], ci[nt][1], a.x, bb.y);
-        dmma884(cr[nt][0], cr[nt][1], -a.y, bb.y);
-        dmma884(ci[nt][0], ci[nt][1], a.y, bb.x);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) VTs[(nt * 8 + 2 * fk + e) * ALDVT + mt * 8 + fr] = make_double2(cr[nt][e], ci[nt][e]);
-  }
-  __syncthreads();                                    // Ts (aliasing the tile buffers) is dead from here on
   auto load_tile = [&](int t, int buf) {
     cplx* dst = Zs + buf * ANC * ALDZ;
     const int col0 = cstart + t * ANC;
@@ -1273,8 +1265,8 @@ int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream) {
     attr_set[h->device & 63] = true;
   }
   dim3 grid(nblk, B);
-  band_tfactor_kernel<<<grid, 256, smem, stream>>>(h->V, h->band_tau, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev, n, bw,
-                                                   g, h->band_KT, nblk, mask);
+  band_tfactor_kernel<<<grid, 256, smem, stream>>>(h->V, h->band_tau, h->band_T, h->band_VT, h->band_blk_s0_dev,
+                                                   h->band_blk_k_dev, n, bw, g, h->band_KT, nblk, mask);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }
@@ -1303,7 +1295,7 @@ int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
       // column parts per block: enough CTAs for ~4 waves, as few as possible (each CTA rebuilds V T)
       const int nparts = std::max(2, std::min(8, (4 * h->nsm + nsub * B - 1) / (nsub * B)));
       dim3 grid(nparts, nsub, B);
-      band_apply_kernel<<<grid, ATH, APPLY_SMEM, h->stream>>>(Z, h->V, h->band_T, h->band_blk_s0_dev, h->band_blk_k_dev,
+      band_apply_kernel<<<grid, ATH, APPLY_SMEM, h->stream>>>(Z, h->V, h->band_VT, h->band_blk_s0_dev, h->band_blk_k_dev,
                                                                h->band_wave_dev + w0, h->halfflag, n, bw, g, nblk, c_lo,
                                                                half ? 1 : 0, mask);
       DW_LAUNCH_CHECK(h);

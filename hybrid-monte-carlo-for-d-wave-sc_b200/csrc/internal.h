@@ -132,6 +132,7 @@ struct Handle {
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase)
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
   cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
+  cplx* band_VT = nullptr;      // device [nblk*32*128*B]: V T per block (fused back-transformation), or null
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
   alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
   bool band_tmap_set = false;
