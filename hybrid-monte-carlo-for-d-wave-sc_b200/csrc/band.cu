@@ -1161,6 +1161,13 @@ int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx*
   return DWHMC_OK;
 }
 
+// The CTAs of a chase launch wait on each other, so two chase launches must never share the GPU half-resident
+// (two handles driven from two host threads would otherwise be able to deadlock).  Launches of one process on
+// one device are chained through an event: each waits for the previous one, whichever handle issued it.
+#include <mutex>
+static std::mutex g_chase_mutex;
+static cudaEvent_t g_chase_done[64] = {};
+
 // launch helper: P persistent CTAs per chain, all co-resident (cooperative launch), chains in slices if needed
 template <class Launch>
 static int chase_launch_loop(Handle* h, Mask mask, const void* kern, size_t smem, Launch launch) {
@@ -1172,6 +1179,11 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, size_t smem
   int P = std::max(1, std::min(4, cap / B));
   if (const char* e = getenv("DWHMC_BAND_P")) P = std::max(1, std::min(atoi(e), cap));
   const int per_launch = std::max(1, cap / P);                    // chains per launch
+  std::lock_guard<std::mutex> lock(g_chase_mutex);
+  cudaEvent_t& done = g_chase_done[h->device & 63];
+  if (!done) DW_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  else DW_CUDA(h, cudaStreamWaitEvent(h->stream, done, 0));
+  struct Rec { cudaEvent_t e; cudaStream_t s; ~Rec() { cudaEventRecord(e, s); } } rec{done, h->stream};
   for (int c0 = 0; c0 < B; c0 += per_launch) {
     ChaseArgs a;
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;

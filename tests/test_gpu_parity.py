@@ -677,3 +677,45 @@ def test_scan_drivers_config4(dw, tmp_path):
     assert rate[2] >= 0.9 and rate[2] >= rate[0] - 0.05
     assert np.allclose(eff, rate / Nts)
 
+
+
+def test_two_handles_concurrently(dw):
+    """Two handles on one GPU driven from two host threads (handles are independent): the cooperative chase
+    launches of the band route are chained per device, so they cannot deadlock half-resident; results equal a
+    sequential run."""
+    import threading
+    L, B, Nt = 12, 40, 3
+    N = L * L
+    rng = np.random.default_rng(91)
+
+    def make(seed):
+        cb = dw.ChainBatch(B, L, L)
+        cb.set_params(1.0, -0.35, -1.08, np.linspace(2, 40, B), 0.8, 1.0)
+        w = np.zeros((B, N)); w[:, :7] = 1.0
+        cb.set_disorder(w)
+        r = np.random.default_rng(seed)
+        cb.set_field((r.random((B, 2, N)) - 0.5 + 1j * (r.random((B, 2, N)) - 0.5)) * 0.1)
+        cb.init_static_H(); cb.update_H_BdG(); cb.diagonalize_H_BdG(); cb.seed(seed)
+        return cb
+
+    dt = np.full(B, 0.05)
+    ref = []
+    for seed in (1, 2):
+        cb = make(seed)
+        ref.append(cb.run_sweeps(3, Nt, dt)[1].copy())
+        cb.close()
+    cbs = [make(1), make(2)]
+    out = [None, None]
+
+    def work(i):
+        out[i] = cbs[i].run_sweeps(3, Nt, dt)[1].copy()
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert all(not t.is_alive() for t in th), "concurrent handles hung"
+    for i in range(2):
+        assert np.allclose(out[i], ref[i], rtol=0, atol=1e-9 * np.max(np.abs(ref[i])) + 1e-9)
+        cbs[i].close()
