@@ -719,3 +719,36 @@ def test_two_handles_concurrently(dw):
     for i in range(2):
         assert np.allclose(out[i], ref[i], rtol=0, atol=1e-9 * np.max(np.abs(ref[i])) + 1e-9)
         cbs[i].close()
+
+
+@pytest.mark.parametrize("hemv", ["1", "0", "2"])
+def test_dense_route_and_hemv_variants(dw, monkeypatch, hemv):
+    """The dense eigensolver route (DWHMC_BAND=0: blocked tridiagonalisation + back-transformation; the route of
+    lattices without a compile-time chase kernel, e.g. L = 32) with each trailing-matrix-product kernel
+    (DWHMC_HEMV: 1 register path, 0 shared-memory staged, 2 persistent warp rings) against the oracle."""
+    monkeypatch.setenv("DWHMC_BAND", "0")
+    monkeypatch.setenv("DWHMC_HEMV", hemv)
+    cb, ps, sts, cs = make_batch(dw, 12, [3.0, 30.0, 300.0], 0.05, 2100)
+    monkeypatch.delenv("DWHMC_BAND"); monkeypatch.delenv("DWHMC_HEMV")
+    assert cb.band_halfwidth() == 0
+    n = 2 * 144
+    E, U = cb.get_eigenvalues(), cb.get_eigenvectors()
+    cb.compute_forces()
+    F = cb.get_forces()
+    for b in range(3):
+        Hf = orc.full_hermitian(cs[b]); Ub = U[b].T
+        nrm = np.max(np.abs(cs[b].E_n))
+        assert np.max(np.abs(E[b] - cs[b].E_n)) <= 1e-12 * nrm
+        assert np.max(np.abs(Hf @ Ub - Ub * E[b])) <= 1e-12 * nrm
+        assert np.max(np.abs(Ub.conj().T @ Ub - np.eye(n))) <= 1e-12
+        orc.compute_forces(cs[b], ps[b], sts[b])
+        assert rel(F[b].T, cs[b].forces) <= RTOL
+    cb.close()
+
+
+def test_default_route_is_band_where_a_chase_kernel_exists(dw):
+    for L, expect in ((4, 0), (8, 36), ((6, 10), 28), (12, 52), (24, 100)):
+        Lx, Ly = (L, L) if isinstance(L, int) else L
+        cb = dw.ChainBatch(1, Lx, Ly)
+        assert cb.band_halfwidth() == expect, (L, cb.band_halfwidth())
+        cb.close()
