@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
 // staircase) and VT = Vb T (from band_tfactor_kernel) stay in shared memory; the CTA walks its column tiles of 16 with cp.async double
 // buffering and runs two products per tile on the FP64 tensor cores (DMMA m8n8k4, four real DMMAs per complex
 // product):   W1 = Vb^H Zt (32 x 16, K = 128),   Zt - VT W1 (128 x 16, K = 32) written straight to global memory.
-// Blocks of one wavefront t = 2 (Gmax - G) + k touch disjoint rows and only depend on smaller t.
+// Blocks of one wavefront t = (Gmax - G) + k touch disjoint rows and only depend on smaller t.
 constexpr int AR = 128, AG = 32, ANC = 16;
 // leading dimensions chosen per access pattern (16-byte elements, eight lanes per wavefront): operands read as
 // (row = lane / 4, k = lane % 4) need ld = 4 mod 8, operands read as (k = lane % 4, row = lane / 4) need ld = 2 mod 4
@@ -1132,13 +1132,15 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
   }
   h->band_blk_s0 = bs0;
   h->band_blk_k = bk;
-  // wavefronts of mutually independent blocks: t = 2 (ngrp - 1 - G) + k (every dependency has a smaller t)
+  // wavefronts of mutually independent blocks: t = (ngrp - 1 - G) + k.  Block (G, k) has to come after (G+1, k),
+  // (G+1, k-1), (G+2, k-1), ... (later sweep groups whose rows overlap) and after (G, k-1): all have a smaller t;
+  // blocks with equal t, (G, k) and (G-j, k-j), touch disjoint rows.
   {
     const int nb2 = (int)bs0.size();
     std::vector<int> tval(nb2), order(nb2);
     int tmax = 0;
     for (int i = 0; i < nb2; ++i) {
-      tval[i] = 2 * (ngrp - 1 - bs0[i] / g) + bk[i];
+      tval[i] = (ngrp - 1 - bs0[i] / g) + bk[i];
       order[i] = i;
       tmax = std::max(tmax, tval[i]);
     }

@@ -153,3 +153,43 @@ def backtransform_blocked(Z, V, TAU, b, g):
             Z[rlo:rlo + rows] -= Vb @ (T @ (Vb.conj().T @ Z[rlo:rlo + rows]))
             k += 1
     return Z
+
+
+def backtransform_wavefronts(Z, V, TAU, b, g):
+    """Same product with the blocks applied wavefront by wavefront, t = (ngrp - 1 - G) + k (the launch order of
+    band_apply_kernel): blocks of one wavefront touch disjoint rows, every dependency has a smaller t."""
+    n = Z.shape[0]
+    Z = Z.astype(complex).copy()
+    ngrp = (n - 1 + g - 1) // g
+    blocks = []
+    for G in range(ngrp):
+        s0 = G * g
+        k = 0
+        while True:
+            rlo = s0 + 1 + k * b
+            if n - rlo < 1 or (k > 0 and n - rlo < 2):
+                break
+            blocks.append(((ngrp - 1 - G) + k, G, k))
+            k += 1
+    for t in sorted({blk[0] for blk in blocks}):
+        wave = [blk for blk in blocks if blk[0] == t]
+        touched = []
+        for _, G, k in wave:
+            s0 = G * g
+            gg = min(g, n - 1 - s0)
+            rlo = s0 + 1 + k * b
+            rows = min(n - rlo, b + gg - 1)
+            assert all(rlo + rows <= lo or hi <= rlo for lo, hi in touched), "blocks of a wavefront overlap"
+            touched.append((rlo, rlo + rows))
+            Vb = np.zeros((rows, gg), complex)
+            for c in range(gg):
+                lo, hi = c, min(c + b, rows)
+                Vb[lo:hi, c] = V[rlo + lo:rlo + hi, s0 + c]
+            T = np.zeros((gg, gg), complex)
+            for i in range(gg):
+                T[i, i] = TAU[s0 + i, k]
+                if i > 0:
+                    T[:i, i] = -TAU[s0 + i, k] * (T[:i, :i] @ (Vb[:, :i].conj().T @ Vb[:, i]))
+            Z[rlo:rlo + rows] -= (Vb @ T) @ (Vb.conj().T @ Z[rlo:rlo + rows])
+    return Z
+

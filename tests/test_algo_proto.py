@@ -48,3 +48,5 @@ def test_band_route_prototype_matches_lapack():
         U = apb.backtransform_blocked(Z, V, TAU, b, g)
         assert np.max(np.abs(Hp @ U - U * w)) <= 1e-12 * np.max(np.abs(w))
         assert np.max(np.abs(U.conj().T @ U - np.eye(n))) <= 1e-12
+        Uw = apb.backtransform_wavefronts(Z, V, TAU, b, g)          # the launch order of the fused kernel
+        assert np.max(np.abs(Uw - U)) <= 1e-13
