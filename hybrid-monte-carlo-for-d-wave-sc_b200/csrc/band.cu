@@ -7,11 +7,15 @@
 //   assemble_band   H straight into lower band storage  AB[d + j LD] = H[j + d, j], LD = 2b
 //   chase           band -> real tridiagonal by Householder bulge chasing (Lang's algorithm):
 //                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; a persistent CTA per sweep
-//                   in flight, sweeps of a chain pipelined three steps apart through release/acquire
-//                   progress counters; the block pushed out by a step stays in shared memory for
-//                   the next one (3 b^2 elements of global traffic per step)
+//                   in flight, sweeps of a chain pipelined through release/acquire progress counters
+//                   (two steps apart in chase_tma_kernel, three in the generic chase_kernel); the
+//                   block pushed out by a step stays in shared memory for the next one (3 b^2
+//                   elements of global traffic per step).  chase_tma_kernel<b, ...> (compile-time b)
+//                   moves the blocks with TMA tensor copies; chase_kernel handles any b <= 101.
 //   tfactor + back-transformation   U = Q2 Z: reflectors of g consecutive sweeps at the same step
-//                   form one staircase block reflector, applied as three DMMA GEMMs (gemm_dmma.cu)
+//                   form one staircase block reflector; band_apply_kernel applies a wavefront of
+//                   independent blocks per launch on the FP64 tensor cores (fallback: three DMMA
+//                   GEMMs per block through gemm_dmma.cu)
 //   unpermute       rows back to the reference's site order
 // The numerics (LAPACK-style zlarfg / zhetd2 updates, application order of the blocks) are the
 // ones prototyped against LAPACK in tests/algo_proto_band.py.
