@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
 constexpr int AR = 128, AG = 32, ANC = 16;
 // leading dimensions chosen per access pattern (16-byte elements, eight lanes per wavefront): operands read as
 // (row = lane / 4, k = lane % 4) need ld = 4 mod 8, operands read as (k = lane % 4, row = lane / 4) need ld = 2 mod 4
-constexpr int ALDV = 132, ALDVT = 130, ALDT = 34, ALDZ = 132, ALDW = 36;
+constexpr int ALDV = 132, ALDVT = 130, ALDZ = 132, ALDW = 36;
 constexpr int ATH = 512;             // 16 warps: four per scheduler keep the tensor pipe fed across barriers
 constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)AG * ALDV + AG * ALDVT + 2 * ANC * ALDZ + 2 * ANC * ALDW);
 
@@ -974,7 +974,6 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
   };
   load_tile(t0, 0);
   const int kmax = (rows + 3) & ~3;                   // K range of the first product (rows beyond are zero)
-  const int khalf = min(kmax, ((kmax / 2 + 7) / 8) * 8);
   for (int t = t0; t < t1; ++t) {
     const int buf = (t - t0) & 1;
     asm volatile("cp.async.wait_group 0;\n" ::);
@@ -985,7 +984,10 @@ __global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Z
     //      alternating k-steps keep four independent DMMA chains in flight
     {
       const int mt = warp & 3, nt = (warp >> 2) & 1, kh = warp >> 3;
-      const int kb = kh ? khalf : 0, ke = kh ? kmax : khalf;
+      // reflectors 8 mt .. 8 mt + 7 are non-zero on rows 8 mt .. 8 mt + 6 + b only (staircase)
+      const int klo = mt * 8, khi = min(kmax, (mt * 8 + 7 + b + 3) & ~3);
+      const int kmid = min(khi, klo + (((khi - klo) / 2 + 7) & ~7));
+      const int kb = kh ? kmid : klo, ke = kh ? khi : kmid;
       double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0, dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
       const cplx* ap = Vs + (mt * 8 + fr) * ALDV + fk;
       const cplx* bp = Zt + (nt * 8 + fr) * ALDZ + fk;
