@@ -592,8 +592,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
         for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
       } else {
         // ---- C. carried block, updated in place, then written back by the bulk-copy engine
-        cplx c = zero;
-        for (int i = tid; i < ln; i += CT) cfmac(c, vs[i], tu[i]);
+        // (v^H tu rides along as column TB of the partial sums: LDP = TB + 1)
         if (act) {
 #pragma unroll
           for (int cc = 0; cc < CB; ++cc) {
@@ -602,14 +601,21 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
             for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
             part[ri * LDP + cj + cc * TC] = acc;
           }
+          if (cj == 0) {
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR < ln) cfmac(acc, vr[q], tu[ri + q * TR]);
+            part[ri * LDP + TB] = acc;
+          }
         }
-        c = block_sum(c, red);
+        __syncthreads();
         PH(1);
         const cplx ctau = cconj(tau);
         for (int j = tid; j < TB; j += CT) {
-          cplx z = part[j];
+          cplx z = part[j], c = part[TB];
 #pragma unroll 5
-          for (int q = 1; q < TR; ++q) z = cadd(z, part[q * LDP + j]);
+          for (int q = 1; q < TR; ++q) { z = cadd(z, part[q * LDP + j]); c = cadd(c, part[q * LDP + TB]); }
           cfms(z, c, cconj(vp[j]));
           wc[j] = cmul(ctau, z);
         }
