@@ -543,11 +543,15 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
 #pragma unroll 5
           for (int q = 1; q < TC; ++q) u = cadd(u, part[q * LDP + i]);
           us[i] = u;
+          // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
+          const cplx t = cmul(taup, u);
+          tu[i] = t;
+          xs[i] = csub(Bc[i], t);
         }
-        __syncthreads();
       }
       PH(0);
       if (k > 0 && ln <= 1) {
+        __syncthreads();
         for (int idx = tid; idx < ln * TB; idx += CT) {
           const int i = idx % ln, j = idx / ln;
           cplx a = Bc[j * LDB + i];
@@ -571,12 +575,6 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
       // ---- A. column to annihilate
       if (k == 0) {
         for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
-      } else {
-        for (int i = tid; i < ln; i += CT) {
-          const cplx t = cmul(taup, us[i]);
-          tu[i] = t;
-          xs[i] = csub(Bc[i], t);
-        }
       }
       __syncthreads();
       // ---- B. reflector
