@@ -1111,6 +1111,13 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
     }
   }
   bw = std::max(bw, 2);
+  // A band of half-width bw is also a band of any larger half-width: round up to the next width with a compile-time
+  // chase kernel (odd sides, L = 22, ...) as long as the matrix is still clearly wider than the band.
+  for (int cand = bw; cand <= 100; ++cand)
+    if (dw_band_has_tma_kernel(cand)) {
+      if (3 * cand <= n) bw = cand;
+      break;
+    }
   // Default wherever a compile-time TMA chase kernel exists for this bandwidth (faster than the dense route at
   // every size measured, 12 <= L <= 24); DWHMC_BAND=0 forces the dense route, DWHMC_BAND=1 the band route (with
   // the generic chase kernel if need be).

@@ -296,7 +296,7 @@ def test_particle_hole_shortcut_and_fallback(dw, monkeypatch):
     cb.close()
 
 
-@pytest.mark.parametrize("L,B", [((6, 10), 3), ((10, 6), 2), (8, 150)])
+@pytest.mark.parametrize("L,B", [((6, 10), 3), ((10, 6), 2), (8, 150), ((5, 13), 2), (9, 2), (22, 2)])
 def test_band_route_shapes(dw, monkeypatch, L, B):
     """Band route on rectangular lattices (the short ring is the fast index of the fold ordering either way) and on
     a batch larger than one cooperative launch of the chase kernel can hold (148 CTAs): spectrum and correlators
@@ -747,7 +747,7 @@ def test_dense_route_and_hemv_variants(dw, monkeypatch, hemv):
 
 
 def test_default_route_is_band_where_a_chase_kernel_exists(dw):
-    for L, expect in ((4, 0), (8, 36), ((6, 10), 28), (12, 52), (24, 100)):
+    for L, expect in ((4, 0), (8, 36), ((6, 10), 28), (12, 52), (24, 100), (22, 100), (9, 44), ((5, 13), 28), (7, 0)):
         Lx, Ly = (L, L) if isinstance(L, int) else L
         cb = dw.ChainBatch(1, Lx, Ly)
         assert cb.band_halfwidth() == expect, (L, cb.band_halfwidth())
