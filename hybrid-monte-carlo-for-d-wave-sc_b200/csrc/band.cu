@@ -210,9 +210,15 @@ __global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
   const int mv_row = tid % rpad, mv_part = tid / rpad;
   const int PS = 32 * RQ;
 
+#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
   const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
 #define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+  constexpr bool prof = false;
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#define PH(i) do { } while (0)
+#endif
   for (int s = p; s < n - 1; s += g.P) {
     int k = 0, r0 = s + 1;
     cplx taup = zero;                                // tau of the previous step (carried block pending)
@@ -495,9 +501,15 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
   unsigned ephase = 0;                               // parity of the next-block barrier
   bool store_pending = false;
 
+#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
   const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
 #define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+  constexpr bool prof = false;
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#define PH(i) do { } while (0)
+#endif
   for (int s = p; s < n - 1; s += g.P) {
     int k = 0, r0 = s + 1;
     cplx taup = zero;
@@ -570,6 +582,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
 #pragma unroll
         for (int q = 0; q < RB; ++q) {
           const int i = ri + q * TR, j = cj + c * TC;
+          if (q * TR + TR - 1 < c * TC) continue;      // sub-block wholly above the diagonal: never referenced
           dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
         }
       // ---- A. column to annihilate
@@ -663,6 +676,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
             const cplx vj = (j < ln) ? vs[j] : zero;
 #pragma unroll
             for (int q = 0; q < RB; ++q) {
+              if (q * TR + TR - 1 < cc * TC) continue;
               cplx a = dreg[q][cc];
               if (ri + q * TR == j) a.y = 0.0;
               cfma(acc[q], a, vj);
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
             cplx acc = zero;
 #pragma unroll
             for (int q = 0; q < RB; ++q)
-              if (ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
+              if (q * TR + TR - 1 >= cc * TC && ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
             part[ri * LDP + j] = acc;
           }
         }
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
 #pragma unroll
           for (int q = 0; q < RB; ++q) {
             const int i = ri + q * TR;
-            if (i >= j && i < ln) {
+            if (q * TR + TR - 1 >= cc * TC && i >= j && i < ln) {
               cplx a = dreg[q][cc];
               if (i == j) a.y = 0.0;
               cfms(a, vr[q], cwj);
@@ -767,6 +781,413 @@ __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __g
   }
   if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
 #undef PH
+}
+
+// ---- TMA chase kernel with a helper warp -------------------------------------------------------------------
+// Same arithmetic as chase_tma_kernel.  Everything that waits on the memory system -- the progress poll of the
+// previous sweep, the tensor copies of the carried block (store, wait, fetch of the next block), the re-read of
+// the corner element, the fence + release that publishes a step -- is done by lane 0 of a 17th warp, so the 512
+// compute threads only ever wait on named barriers the helper has usually reached already:
+//   barrier 1  compute threads only (the former __syncthreads)
+//   barrier 2  "ready":      helper arrives (poll passed, block landed, corner patched) -> compute threads wait
+//   barrier 3  "Bc written": compute threads arrive -> helper waits, then stores the block and fetches the next
+//   barrier 4  "D stored":   compute threads arrive -> helper waits, then fences and publishes the step
+template <int NC> __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
+template <int NC> __device__ __forceinline__ void hbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NC + 32) : "memory"); }
+template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NC + 32) : "memory");
+}
+template <int NC> __device__ __forceinline__ cplx block_sum_c(cplx v, cplx* red) {        // block_sum over the compute threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  csync<NC>();
+  if (lane == 0) red[warp] = v;
+  csync<NC>();
+  cplx t = make_double2(0.0, 0.0);
+  for (int i = 0; i < NC / 32; ++i) t = cadd(t, red[i]);
+  return t;
+}
+template <int NC> __device__ __forceinline__ void larfg_block_c(const cplx* xs, cplx* vs, int ln, cplx* red, cplx& tau, double& beta) {
+  const int tid = threadIdx.x;
+  cplx nrm = make_double2(0.0, 0.0);
+  for (int i = 1 + tid; i < ln; i += NC) { const cplx a = xs[i]; nrm.x += a.x * a.x + a.y * a.y; }
+  nrm = block_sum_c<NC>(nrm, red);
+  const cplx alpha = xs[0];
+  cplx scale;
+  if (nrm.x == 0.0 && alpha.y == 0.0) {
+    beta = alpha.x;
+    tau = make_double2(0.0, 0.0);
+    scale = make_double2(0.0, 0.0);
+  } else {
+    beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm.x), alpha.x);
+    tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+    const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+    scale = make_double2(dr / den, -di / den);
+  }
+  for (int i = tid; i < ln; i += NC) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
+  csync<NC>();
+}
+
+__host__ __device__ constexpr int chase_nc(int tr, int tc) { return (tr * tc + 31) / 32 * 32; }
+
+template <int TB, int TR, int TC, int RB, int CB>
+__global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmap) {
+  constexpr int NC = chase_nc(TR, TC);           // compute threads (whole warps); the helper warp follows
+  static_assert(TR * RB == TB && TC * CB >= TB && TC * (CB - 1) < TB && TB <= NC && NC + 32 <= 512, "cover, at most 16 warps");
+  constexpr bool XC = TC * CB == TB;             // exact column cover; otherwise the last column of a thread may not exist
+#define JV(cc) (XC || (cc) < CB - 1 || cj + (cc) * TC < TB)
+  constexpr int LDB = TB;        // dense box layout of the tensor copies
+  constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
+  constexpr int LD = 2 * TB;
+  constexpr int NP = (TR > TC) ? TR : TC;
+  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
+  if (!g.mask.on(chain)) return;
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  const int n = g.n;
+  cplx* Bc = reinterpret_cast<cplx*>(smem_tma);      // [TB][LDB]
+  cplx* vs = Bc + LDB * TB;
+  cplx* vp = vs + TB;
+  cplx* us = vp + TB;
+  cplx* xs = us + TB;
+  cplx* tu = xs + TB;
+  cplx* wc = tu + TB;
+  cplx* part = wc + TB;                              // [NP][LDP]
+  cplx* red = part + NP * LDP;                       // [32]
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
+  const int tid = threadIdx.x;
+  cplx* AB = g.AB + (size_t)chain * n * LD;
+  int* prog = g.prog + (size_t)chain * n;
+  if (tid == 0) mbar_init(bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  unsigned ephase = 0;                               // parity of the next-block barrier
+
+  if (tid >= NC) {
+    // ================= helper warp =================
+    const bool l0 = tid == NC;
+    bool store_pending = false, publish_pending = false;
+    int pub_s = 0, pub_v = 0;
+    for (int s = p; s < n - 1; s += g.P) {
+      int k = 0, r0 = s + 1, lcar = 0;
+      while (true) {
+        const int ln = min(TB, n - r0);
+        if (l0) {
+          if (s > 0) {
+            const int need = k + 2;
+            while (ld_acquire(prog + s - 1) < need) __nanosleep(20);
+          }
+          if (k > 0) {
+            mbar_wait(bar, ephase);
+            if (lcar == TB) Bc[(TB - 1) * LDB + TB - 1] = ldg2(AB + (size_t)(r0 - 1) * LD + TB);
+          }
+        }
+        if (k > 0) ephase ^= 1;
+        __syncwarp();
+        if (publish_pending) hbar_sync<NC>(4);             // the diagonal block of the previous step is stored
+        hbar_arrive<NC>(2);                                // this step may start
+        if (publish_pending) {
+          if (l0) {
+            if (store_pending) bulk_wait_all();        // write-back performed in global memory
+            fence_async();
+            __threadfence();
+            st_release(prog + pub_s, pub_v);
+          }
+          store_pending = false;
+          publish_pending = false;
+        }
+        if (k > 0 && ln <= 1) break;
+        if (k > 0) {
+          hbar_sync<NC>(3);                                // carried block updated in shared memory
+          if (l0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(&tmap), "r"(2 * r0), "r"(r0 - TB), "r"(chain), "r"(smem_u32(Bc)) : "memory");
+            bulk_commit();
+          }
+          store_pending = true;
+        }
+        const int r1 = r0 + ln;
+        const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
+        if (l0) {
+          if (store_pending) bulk_wait_read();         // the write-back has finished reading Bc
+          if (l2 > 0) {
+            fence_async();
+            mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(Bc)), "l"(&tmap), "r"(2 * r1), "r"(r0), "r"(chain), "r"(smem_u32(bar)) : "memory");
+          }
+        }
+        if (l2 == 0) break;
+        publish_pending = true; pub_s = s; pub_v = k + 1;
+        lcar = l2;
+        r0 = r1;
+        ++k;
+      }
+      hbar_sync<NC>(4);                                    // all writes of the sweep issued
+      if (l0) {
+        if (store_pending) bulk_wait_all();
+        fence_async();
+        __threadfence();
+        st_release(prog + s, 1 << 30);
+      }
+      store_pending = false;
+      publish_pending = false;
+    }
+    return;
+  }
+
+  // ================= compute threads =================
+  const bool act = tid < TR * TC;
+  const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
+  const int soff = cj * LDB + ri;
+  const int goff = cj * (LD - 1) + ri;
+  cplx* V = g.V + (size_t)chain * n * n;
+  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
+  const cplx zero = make_double2(0.0, 0.0);
+#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
+#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+  constexpr bool prof = false;
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#define PH(i) do { } while (0)
+#endif
+  for (int s = p; s < n - 1; s += g.P) {
+    int k = 0, r0 = s + 1;
+    cplx taup = zero;
+    int lcar = 0;                                    // rows of the carried block in Bc
+    while (true) {
+      const int ln = min(TB, n - r0);
+      if (prof) tlast = clock64();
+      hbar_sync<NC>(2);                                  // sweep s-1 two steps ahead, carried block landed and patched
+      PH(7);
+      if (k > 0) {
+        mbar_wait(bar, ephase);                      // completed already: makes the bulk copy visible to this thread
+        ephase ^= 1;
+        if (act) {
+          cplx acc[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const cplx vj = vp[cj + cc * TC];
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR < lcar) cfma(acc[q], Bc[soff + cc * TC * LDB + q * TR], vj);
+          }
+#pragma unroll
+          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
+        }
+        csync<NC>();
+        for (int i = tid; i < lcar; i += NC) {
+          cplx u = part[i];
+#pragma unroll 5
+          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * LDP + i]);
+          us[i] = u;
+          // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
+          const cplx t = cmul(taup, u);
+          tu[i] = t;
+          xs[i] = csub(Bc[i], t);
+        }
+      }
+      PH(0);
+      if (k > 0 && ln <= 1) {
+        csync<NC>();
+        for (int idx = tid; idx < ln * TB; idx += NC) {
+          const int i = idx % ln, j = idx / ln;
+          cplx a = Bc[j * LDB + i];
+          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
+          stg2(AB + (size_t)(r0 - TB + j) * LD + (TB + i - j), a);
+        }
+        for (int i = tid; i < ln; i += NC) V[(size_t)s * n + r0 + i] = zero;
+        break;
+      }
+      // ---- prefetch the lower triangle of the diagonal block into registers
+      cplx* baseD = AB + (size_t)r0 * LD + goff;
+      cplx dreg[RB][CB];
+#pragma unroll
+      for (int c = 0; c < CB; ++c)
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          const int i = ri + q * TR, j = cj + c * TC;
+          if (q * TR + TR - 1 < c * TC) continue;      // sub-block wholly above the diagonal: never referenced
+          dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
+        }
+      // ---- A. column to annihilate
+      if (k == 0) {
+        for (int i = tid; i < ln; i += NC) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
+      }
+      csync<NC>();
+      // ---- B. reflector
+      cplx tau; double beta;
+      larfg_block_c<NC>(xs, vs, ln, red, tau, beta);
+      PH(2);
+      for (int i = tid; i < ln; i += NC) V[(size_t)s * n + r0 + i] = vs[i];
+      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
+      cplx vr[RB];
+#pragma unroll
+      for (int q = 0; q < RB; ++q) vr[q] = (ri + q * TR < ln) ? vs[ri + q * TR] : zero;
+      if (k == 0) {
+        for (int i = tid; i < ln; i += NC) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
+      } else {
+        // ---- C. carried block, updated in place; the helper writes it back with the bulk-copy engine
+        // (v^H tu rides along as column TB of the partial sums: LDP = TB + 1)
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
+            part[ri * LDP + cj + cc * TC] = acc;
+          }
+          if (cj == 0) {
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR < ln) cfmac(acc, vr[q], tu[ri + q * TR]);
+            part[ri * LDP + TB] = acc;
+          }
+        }
+        csync<NC>();
+        PH(1);
+        const cplx ctau = cconj(tau);
+        for (int j = tid; j < TB; j += NC) {
+          cplx z = part[j], c = part[TB];
+#pragma unroll 5
+          for (int q = 1; q < TR; ++q) { z = cadd(z, part[q * LDP + j]); c = cadd(c, part[q * LDP + TB]); }
+          cfms(z, c, cconj(vp[j]));
+          wc[j] = cmul(ctau, z);
+        }
+        csync<NC>();
+        if (act) {
+          cplx tur[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) tur[q] = tu[min(ri + q * TR, TB - 1)];
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const int j = cj + cc * TC;
+            const cplx cvp = cconj(vp[j]), wj = wc[j];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+              const int i = ri + q * TR;
+              if (i < ln) {
+                cplx o = Bc[soff + cc * TC * LDB + q * TR];
+                cfms(o, tur[q], cvp);
+                cfms(o, vr[q], wj);
+                if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
+                Bc[soff + cc * TC * LDB + q * TR] = o;
+              }
+            }
+          }
+        }
+        fence_async();                                // generic-proxy writes of Bc -> visible to the bulk engine
+        hbar_arrive<NC>(3);
+      }
+      PH(3);
+      // ---- D. diagonal block from registers: x = tau D v, D Hermitian (lower part held)
+      {
+        // row part: sum_{j <= i} D[i,j] v[j]
+        if (act) {
+          cplx acc[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            const int j = cj + cc * TC;
+            const cplx vj = (j < ln) ? vs[j] : zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+              if (q * TR + TR - 1 < cc * TC) continue;
+              cplx a = dreg[q][cc];
+              if (ri + q * TR == j) a.y = 0.0;
+              cfma(acc[q], a, vj);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
+        }
+        csync<NC>();
+        for (int i = tid; i < ln; i += NC) {
+          cplx wv = part[i];
+#pragma unroll 5
+          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * LDP + i]);
+          xs[i] = wv;
+        }
+        csync<NC>();
+        // column part: sum_{i > j} conj(D[i,j]) v[i]
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const int j = cj + cc * TC;
+            cplx acc = zero;
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (q * TR + TR - 1 >= cc * TC && ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
+            part[ri * LDP + j] = acc;
+          }
+        }
+        csync<NC>();
+        cplx dot = zero;
+        for (int i = tid; i < ln; i += NC) {
+          cplx wv = xs[i];
+#pragma unroll 5
+          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * LDP + i]);
+          wv = cmul(tau, wv);
+          xs[i] = wv;
+          cfmac(dot, wv, vs[i]);
+        }
+        dot = block_sum_c<NC>(dot, red);
+        cplx alpha = cmul(tau, dot);
+        alpha.x *= -0.5; alpha.y *= -0.5;
+        for (int i = tid; i < ln; i += NC) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
+        csync<NC>();
+      }
+      PH(4);
+      const int r1 = r0 + ln;
+      const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
+      // ---- D update and store (lower part, from registers)
+      if (act) {
+        cplx wr[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) wr[q] = xs[min(ri + q * TR, TB - 1)];
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          if (!JV(cc)) continue;
+          const int j = cj + cc * TC;
+          const cplx cwj = cconj(xs[j]), cvj = cconj(vs[j]);
+#pragma unroll
+          for (int q = 0; q < RB; ++q) {
+            const int i = ri + q * TR;
+            if (q * TR + TR - 1 >= cc * TC && i >= j && i < ln) {
+              cplx a = dreg[q][cc];
+              if (i == j) a.y = 0.0;
+              cfms(a, vr[q], cwj);
+              cfms(a, wr[q], cvj);
+              if (i == j) a.y = 0.0;
+              stg2(baseD + cc * TC * (LD - 1) + q * TR, a);
+            }
+          }
+        }
+      }
+      if (l2 == 0) break;
+      for (int i = tid; i < ln; i += NC) vp[i] = vs[i];
+      taup = tau;
+      lcar = l2;
+      PH(6);
+      hbar_arrive<NC>(4);
+      r0 = r1;
+      ++k;
+    }
+    hbar_arrive<NC>(4);
+  }
+  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
+#undef PH
+#undef JV
 }
 
 template <int TB, int TR, int TC>
@@ -1189,10 +1610,10 @@ static cudaEvent_t g_chase_done[64] = {};
 
 // launch helper: P persistent CTAs per chain, all co-resident (cooperative launch), chains in slices if needed
 template <class Launch>
-static int chase_launch_loop(Handle* h, Mask mask, const void* kern, size_t smem, Launch launch) {
+static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthreads, size_t smem, Launch launch) {
   const int n = h->n, B = h->B, bw = h->band_b;
   int per_sm = 0;
-  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CT, smem));
+  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
   const int cap = h->nsm * per_sm;
   if (cap < 1) { h->err = "dw_band_chase: kernel does not fit"; return DWHMC_E_CUDA; }
   int P = std::max(1, std::min(4, cap / B));
@@ -1225,9 +1646,12 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, size_t smem
   return DWHMC_OK;
 }
 
-template <int TB, int TR, int TC, int RB, int CB>
+template <bool HELPER, int TB, int TR, int TC, int RB, int CB>
 static int chase_tma_dispatch(Handle* h, Mask mask) {
-  auto kern = chase_tma_kernel<TB, TR, TC, RB, CB>;
+  void (*kern)(ChaseArgs, const CUtensorMap) = nullptr;
+  if constexpr (HELPER) kern = chase_tmah_kernel<TB, TR, TC, RB, CB>;
+  else kern = chase_tma_kernel<TB, TR, TC, RB, CB>;
+  const int nthreads = HELPER ? chase_nc(TR, TC) + 32 : CT;
   const size_t smem = chase_tma_smem<TB, TR, TC>();
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
@@ -1239,9 +1663,9 @@ static int chase_tma_dispatch(Handle* h, Mask mask) {
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap)));
     h->band_tmap_set = true;
   }
-  return chase_launch_loop(h, mask, (const void*)kern, smem, [&](ChaseArgs& a, int ctas) -> int {
+  return chase_launch_loop(h, mask, (const void*)kern, nthreads, smem, [&](ChaseArgs& a, int ctas) -> int {
     void* targs[] = {&a, h->band_tmap};
-    DW_CUDA(h, cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(CT), targs, smem, h->stream));
+    DW_CUDA(h, cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(nthreads), targs, smem, h->stream));
     return DWHMC_OK;
   });
 }
@@ -1256,15 +1680,27 @@ int dw_band_chase(Handle* h, Mask mask) {
   DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * (size_t)n * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
-  if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 20, 4, 5>(h, mask)));
-  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
-  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
-  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));
-  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<60, 15, 20, 4, 3>(h, mask)));
-  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<52, 13, 26, 4, 2>(h, mask)));
-  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<44, 22, 22, 2, 2>(h, mask)));
-  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<36, 18, 18, 2, 2>(h, mask)));
-  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<28, 14, 14, 2, 2>(h, mask)));
+  // DWHMC_BAND_HELPER=0: the variant without the helper warp (every thread waits on the memory system in turn).
+  // With the helper warp the compute threads fill at most 15 warps (16 warps x 128 registers is the register file).
+  static const bool helper = getenv("DWHMC_BAND_HELPER") ? atoi(getenv("DWHMC_BAND_HELPER")) != 0 : true;
+  if (!generic && helper && bw == 100) DW_TRY((chase_tma_dispatch<true, 100, 25, 19, 4, 6>(h, mask)));
+  else if (!generic && helper && bw == 84) DW_TRY((chase_tma_dispatch<true, 84, 21, 21, 4, 4>(h, mask)));
+  else if (!generic && helper && bw == 76) DW_TRY((chase_tma_dispatch<true, 76, 19, 19, 4, 4>(h, mask)));
+  else if (!generic && helper && bw == 68) DW_TRY((chase_tma_dispatch<true, 68, 17, 17, 4, 4>(h, mask)));
+  else if (!generic && helper && bw == 60) DW_TRY((chase_tma_dispatch<true, 60, 15, 20, 4, 3>(h, mask)));
+  else if (!generic && helper && bw == 52) DW_TRY((chase_tma_dispatch<true, 52, 13, 26, 4, 2>(h, mask)));
+  else if (!generic && helper && bw == 44) DW_TRY((chase_tma_dispatch<true, 44, 22, 11, 2, 4>(h, mask)));
+  else if (!generic && helper && bw == 36) DW_TRY((chase_tma_dispatch<true, 36, 18, 18, 2, 2>(h, mask)));
+  else if (!generic && helper && bw == 28) DW_TRY((chase_tma_dispatch<true, 28, 14, 14, 2, 2>(h, mask)));
+  else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<false, 100, 25, 20, 4, 5>(h, mask)));
+  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<false, 84, 21, 21, 4, 4>(h, mask)));
+  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<false, 76, 19, 19, 4, 4>(h, mask)));
+  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<false, 68, 17, 17, 4, 4>(h, mask)));
+  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<false, 60, 15, 20, 4, 3>(h, mask)));
+  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<false, 52, 13, 26, 4, 2>(h, mask)));
+  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<false, 44, 22, 22, 2, 2>(h, mask)));
+  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<false, 36, 18, 18, 2, 2>(h, mask)));
+  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<false, 28, 14, 14, 2, 2>(h, mask)));
   else {
     const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
     static bool attr_set[64] = {false};
@@ -1272,7 +1708,7 @@ int dw_band_chase(Handle* h, Mask mask) {
       DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_set[h->device & 63] = true;
     }
-    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, smem, [&](ChaseArgs& a, int ctas) -> int {
+    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, CT, smem, [&](ChaseArgs& a, int ctas) -> int {
       void* args[] = {&a};
       DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctas), dim3(CT), args, smem, h->stream));
       return DWHMC_OK;
