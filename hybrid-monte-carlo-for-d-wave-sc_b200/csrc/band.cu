@@ -832,11 +832,17 @@ template <int NC> __device__ __forceinline__ void larfg_block_c(const cplx* xs, 
 __host__ __device__ constexpr int chase_nc(int tr, int tc) { return (tr * tc + 31) / 32 * 32; }
 
 template <int TB, int TR, int TC, int RB, int CB>
-__global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmapA,
+                                                                              const __grid_constant__ CUtensorMap tmapB) {
   constexpr int NC = chase_nc(TR, TC);           // compute threads (whole warps); the helper warp follows
   static_assert(TR * RB == TB && TC * CB >= TB && TC * (CB - 1) < TB && TB <= NC && NC + 32 <= 512, "cover, at most 16 warps");
   constexpr bool XC = TC * CB == TB;             // exact column cover; otherwise the last column of a thread may not exist
 #define JV(cc) (XC || (cc) < CB - 1 || cj + (cc) * TC < TB)
+  // The carried block travels in column pieces of two thread-columns each (2 TC matrix columns; the last piece takes
+  // the rest): a piece is written back as soon as it is updated, and its place is refilled from the next block as
+  // soon as the write-back has read it.  tmapA: boxes of 2 TC columns, tmapB: box of the last piece.
+  constexpr int NPIECE = (CB + 1) / 2;
+  constexpr int PW = 2 * TC;
   constexpr int LDB = TB;        // dense box layout of the tensor copies
   constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
   constexpr int LD = 2 * TB;
@@ -897,25 +903,43 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           publish_pending = false;
         }
         if (k > 0 && ln <= 1) break;
-        if (k > 0) {
-          hbar_sync<NC>(3);                                // carried block updated in shared memory
-          if (l0) {
-            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                         ::"l"(&tmap), "r"(2 * r0), "r"(r0 - TB), "r"(chain), "r"(smem_u32(Bc)) : "memory");
-            bulk_commit();
-          }
-          store_pending = true;
-        }
         const int r1 = r0 + ln;
         const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
-        if (l0) {
-          if (store_pending) bulk_wait_read();         // the write-back has finished reading Bc
-          if (l2 > 0) {
-            fence_async();
-            mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(smem_u32(Bc)), "l"(&tmap), "r"(2 * r1), "r"(r0), "r"(chain), "r"(smem_u32(bar)) : "memory");
+        auto store_piece = [&](int pc) {               // rows r0 .. (clipped at n), columns r0-TB+pc PW ..
+          const CUtensorMap* tm = (pc < NPIECE - 1) ? &tmapA : &tmapB;
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                       ::"l"(tm), "r"(2 * r0), "r"(r0 - TB + pc * PW), "r"(chain), "r"(smem_u32(Bc + pc * PW * LDB)) : "memory");
+          bulk_commit();
+        };
+        auto load_piece = [&](int pc) {                // next block: rows r1 .., columns r0+pc PW ..
+          const CUtensorMap* tm = (pc < NPIECE - 1) ? &tmapA : &tmapB;
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                       ::"r"(smem_u32(Bc + pc * PW * LDB)), "l"(tm), "r"(2 * r1), "r"(r0 + pc * PW), "r"(chain), "r"(smem_u32(bar)) : "memory");
+        };
+        if (k > 0) {
+#pragma unroll
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            hbar_sync<NC>(5 + pc);                     // piece pc of the carried block updated in shared memory
+            if (l0) {
+              store_piece(pc);
+              if (l2 > 0 && pc >= 1) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // piece pc-1 has been read
+                if (pc == 1) { fence_async(); mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx))); }
+                load_piece(pc - 1);
+              }
+            }
           }
+          store_pending = true;
+          if (l0 && l2 > 0) {
+            bulk_wait_read();
+            if (NPIECE == 1) { fence_async(); mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx))); }
+            load_piece(NPIECE - 1);
+          }
+        } else if (l0 && l2 > 0) {
+          fence_async();
+          mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));
+#pragma unroll
+          for (int pc = 0; pc < NPIECE; ++pc) load_piece(pc);
         }
         if (l2 == 0) break;
         publish_pending = true; pub_s = s; pub_v = k + 1;
@@ -944,9 +968,11 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   cplx* V = g.V + (size_t)chain * n * n;
   cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
   const cplx zero = make_double2(0.0, 0.0);
-#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#ifdef DWHMC_CHASE_PROF                              // phase clocks of CTA 0 (experiments): accumulators in shared memory
+  __shared__ long long tph[8];
+  long long tlast = 0;
   const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
+  if (prof) for (int i = 0; i < 8; ++i) tph[i] = 0;
 #define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
 #else
   constexpr bool prof = false;
@@ -962,6 +988,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
       if (prof) tlast = clock64();
       hbar_sync<NC>(2);                                  // sweep s-1 two steps ahead, carried block landed and patched
       PH(7);
+      double nrm2 = 0.0;                               // |x[1:]|^2, summed where x is produced
       if (k > 0) {
         mbar_wait(bar, ephase);                      // completed already: makes the bulk copy visible to this thread
         ephase ^= 1;
@@ -989,7 +1016,9 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
           const cplx t = cmul(taup, u);
           tu[i] = t;
-          xs[i] = csub(Bc[i], t);
+          const cplx x = csub(Bc[i], t);
+          xs[i] = x;
+          if (i > 0) nrm2 += x.x * x.x + x.y * x.y;
         }
       }
       PH(0);
@@ -1017,12 +1046,37 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         }
       // ---- A. column to annihilate
       if (k == 0) {
-        for (int i = tid; i < ln; i += NC) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
+        for (int i = tid; i < ln; i += NC) {
+          const cplx x = ldg2(AB + (size_t)s * LD + 1 + i);
+          xs[i] = x;
+          if (i > 0) nrm2 += x.x * x.x + x.y * x.y;
+        }
       }
+      nrm2 = warp_sum(make_double2(nrm2, 0.0)).x;
+      if ((tid & 31) == 0) red[tid >> 5].x = nrm2;
+      PH(5);
       csync<NC>();
-      // ---- B. reflector
+      // ---- B. reflector (LAPACK zlarfg; every thread computes tau, beta and the scale)
       cplx tau; double beta;
-      larfg_block_c<NC>(xs, vs, ln, red, tau, beta);
+      {
+        double nrm = 0.0;
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) nrm += red[w].x;
+        const cplx alpha = xs[0];
+        cplx scale;
+        if (nrm == 0.0 && alpha.y == 0.0) {
+          beta = alpha.x;
+          tau = zero;
+          scale = zero;
+        } else {
+          beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm), alpha.x);
+          tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
+          const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
+          scale = make_double2(dr / den, -di / den);
+        }
+        for (int i = tid; i < ln; i += NC) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
+        csync<NC>();
+      }
       PH(2);
       for (int i = tid; i < ln; i += NC) V[(size_t)s * n + r0 + i] = vs[i];
       if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
@@ -1062,30 +1116,33 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           wc[j] = cmul(ctau, z);
         }
         csync<NC>();
-        if (act) {
+        {
           cplx tur[RB];
 #pragma unroll
           for (int q = 0; q < RB; ++q) tur[q] = tu[min(ri + q * TR, TB - 1)];
 #pragma unroll
           for (int cc = 0; cc < CB; ++cc) {
-            if (!JV(cc)) continue;
-            const int j = cj + cc * TC;
-            const cplx cvp = cconj(vp[j]), wj = wc[j];
+            if (act && JV(cc)) {
+              const int j = cj + cc * TC;
+              const cplx cvp = cconj(vp[j]), wj = wc[j];
 #pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              const int i = ri + q * TR;
-              if (i < ln) {
-                cplx o = Bc[soff + cc * TC * LDB + q * TR];
-                cfms(o, tur[q], cvp);
-                cfms(o, vr[q], wj);
-                if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
-                Bc[soff + cc * TC * LDB + q * TR] = o;
+              for (int q = 0; q < RB; ++q) {
+                const int i = ri + q * TR;
+                if (i < ln) {
+                  cplx o = Bc[soff + cc * TC * LDB + q * TR];
+                  cfms(o, tur[q], cvp);
+                  cfms(o, vr[q], wj);
+                  if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
+                  Bc[soff + cc * TC * LDB + q * TR] = o;
+                }
               }
+            }
+            if ((cc & 1) == 1 || cc == CB - 1) {
+              fence_async();                            // generic-proxy writes of Bc -> visible to the bulk engine
+              hbar_arrive<NC>(5 + cc / 2);              // the helper writes this piece back
             }
           }
         }
-        fence_async();                                // generic-proxy writes of Bc -> visible to the bulk engine
-        hbar_arrive<NC>(3);
       }
       PH(3);
       // ---- D. diagonal block from registers: x = tau D v, D Hermitian (lower part held)
@@ -1141,11 +1198,17 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           xs[i] = wv;
           cfmac(dot, wv, vs[i]);
         }
-        dot = block_sum_c<NC>(dot, red);
-        cplx alpha = cmul(tau, dot);
-        alpha.x *= -0.5; alpha.y *= -0.5;
-        for (int i = tid; i < ln; i += NC) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
+        dot = warp_sum(dot);
+        if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
         csync<NC>();
+      }
+      cplx alpha;                                      // w = y + alpha v, formed where it is used
+      {
+        cplx dsum = zero;
+#pragma unroll
+        for (int w = 0; w < NC / 32; ++w) dsum = cadd(dsum, red[w]);
+        alpha = cmul(tau, dsum);
+        alpha.x *= -0.5; alpha.y *= -0.5;
       }
       PH(4);
       const int r1 = r0 + ln;
@@ -1154,12 +1217,15 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
       if (act) {
         cplx wr[RB];
 #pragma unroll
-        for (int q = 0; q < RB; ++q) wr[q] = xs[min(ri + q * TR, TB - 1)];
+        for (int q = 0; q < RB; ++q) { wr[q] = xs[min(ri + q * TR, TB - 1)]; cfma(wr[q], alpha, vr[q]); }
 #pragma unroll
         for (int cc = 0; cc < CB; ++cc) {
           if (!JV(cc)) continue;
           const int j = cj + cc * TC;
-          const cplx cwj = cconj(xs[j]), cvj = cconj(vs[j]);
+          const cplx vj = vs[j];
+          cplx wj = xs[j];
+          cfma(wj, alpha, vj);
+          const cplx cwj = cconj(wj), cvj = cconj(vj);
 #pragma unroll
           for (int q = 0; q < RB; ++q) {
             const int i = ri + q * TR;
@@ -1197,7 +1263,7 @@ constexpr size_t chase_tma_smem() {
 
 // Tensor map of the band storage of all chains as the skewed view T[chain][c][r] = AB[chain][c LD + (r - c)]
 // = base + chain n LD + c (LD - 1) + r (in complex elements; FP64 element type, so the inner extent is 2 n).
-static int make_band_tensor_map(Handle* h, CUtensorMap* out) {
+static int make_band_tensor_map(Handle* h, CUtensorMap* out, int box_cols) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1211,7 +1277,7 @@ static int make_band_tensor_map(Handle* h, CUtensorMap* out) {
   const cuuint64_t n = (cuuint64_t)h->n, LD = (cuuint64_t)h->band_LD, b = (cuuint64_t)h->band_b;
   const cuuint64_t gdim[3] = {2 * n, n, (cuuint64_t)h->B};
   const cuuint64_t gstr[2] = {(LD - 1) * sizeof(cplx), n * LD * sizeof(cplx)};
-  const cuuint32_t box[3] = {(cuuint32_t)(2 * b), (cuuint32_t)b, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)(2 * b), (cuuint32_t)box_cols, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult rc = reinterpret_cast<EncodeFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, h->A, gdim, gstr, box, estr,
                                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1648,11 +1714,11 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
 
 template <bool HELPER, int TB, int TR, int TC, int RB, int CB>
 static int chase_tma_dispatch(Handle* h, Mask mask) {
-  void (*kern)(ChaseArgs, const CUtensorMap) = nullptr;
-  if constexpr (HELPER) kern = chase_tmah_kernel<TB, TR, TC, RB, CB>;
-  else kern = chase_tma_kernel<TB, TR, TC, RB, CB>;
   const int nthreads = HELPER ? chase_nc(TR, TC) + 32 : CT;
   const size_t smem = chase_tma_smem<TB, TR, TC>();
+  const void* kern = nullptr;
+  if constexpr (HELPER) kern = (const void*)chase_tmah_kernel<TB, TR, TC, RB, CB>;
+  else kern = (const void*)chase_tma_kernel<TB, TR, TC, RB, CB>;
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1660,12 +1726,16 @@ static int chase_tma_dispatch(Handle* h, Mask mask) {
   }
   static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
   if (!h->band_tmap_set) {
-    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap)));
+    constexpr int npiece = (CB + 1) / 2, pw = 2 * TC;      // column pieces of the helper-warp kernel
+    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap), TB));
+    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_a), std::min(pw, TB)));
+    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_b), TB - pw * (npiece - 1)));
     h->band_tmap_set = true;
   }
-  return chase_launch_loop(h, mask, (const void*)kern, nthreads, smem, [&](ChaseArgs& a, int ctas) -> int {
+  return chase_launch_loop(h, mask, kern, nthreads, smem, [&](ChaseArgs& a, int ctas) -> int {
+    void* targs_h[] = {&a, h->band_tmap_a, h->band_tmap_b};
     void* targs[] = {&a, h->band_tmap};
-    DW_CUDA(h, cudaLaunchCooperativeKernel((const void*)kern, dim3(ctas), dim3(nthreads), targs, smem, h->stream));
+    DW_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(nthreads), HELPER ? targs_h : targs, smem, h->stream));
     return DWHMC_OK;
   });
 }

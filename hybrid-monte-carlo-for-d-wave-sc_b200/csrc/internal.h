@@ -135,6 +135,8 @@ struct Handle {
   cplx* band_VT = nullptr;      // device [nblk*32*128*B]: V T per block (fused back-transformation), or null
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
   alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
+  alignas(64) unsigned char band_tmap_a[128] = {};  // the same view with narrower boxes: column pieces of the carried block
+  alignas(64) unsigned char band_tmap_b[128] = {};
   bool band_tmap_set = false;
   // transport / spectra workspace (transport.cu), allocated on first use
   double* tr_work = nullptr; size_t tr_work_count = 0;
