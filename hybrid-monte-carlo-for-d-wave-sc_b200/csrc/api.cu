@@ -170,7 +170,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   if ((rc = dw_band_setup(h, nn, nnn)) != DWHMC_OK) return fail(rc);
   if (h->band_b > 0) {
     const size_t nblk = h->band_blk_s0.size();
-    AL(h->band_pos, (size_t)n); AL(h->band_prog, nB); AL(h->band_tau, nB * h->band_KT);
+    AL(h->band_pos, (size_t)n); AL(h->band_prog, nB + (size_t)B); AL(h->band_tau, nB * h->band_KT);
     AL(h->band_T, nblk * 64 * 64 * B);
     if (h->band_g <= 32 && h->band_b + h->band_g - 1 <= 128) AL(h->band_VT, nblk * 32 * 128 * B);
     AL(h->band_blk_s0_dev, nblk); AL(h->band_blk_k_dev, nblk); AL(h->band_wave_dev, nblk);

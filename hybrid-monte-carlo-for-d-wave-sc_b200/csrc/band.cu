@@ -133,6 +133,7 @@ __global__ void band_scatter_kernel(cplx* __restrict__ ABall, const double* __re
 struct ChaseArgs {
   cplx* AB; cplx* V; cplx* tau2; int* prog;
   int n, b, LD, KT, P, c0;       // c0: first chain of this launch
+  int* next; int B, stride;      // helper-warp kernel: per-chain sweep tickets, chains, rotation stride of the spare CTAs
   Mask mask;
   long long* clk;                // optional [8] phase clock accumulators of CTA 0 (profiling experiments)
 };
@@ -847,8 +848,10 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
   constexpr int LD = 2 * TB;
   constexpr int NP = (TR > TC) ? TR : TC;
-  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
-  if (!g.mask.on(chain)) return;
+  // Sweeps are handed out by a ticket counter per chain: a CTA takes the next sweep of its home chain (CTA i < 2 B:
+  // chain i mod B, for good; the spare CTAs move on by `stride` chains after every sweep), and of the following
+  // chains once that one is exhausted.  Tickets are taken in sweep order and a taken sweep is run at once, so the
+  // sweep a CTA waits for is always in flight on a co-resident CTA (cooperative launch).
   extern __shared__ __align__(128) unsigned char smem_tma[];
   const int n = g.n;
   cplx* Bc = reinterpret_cast<cplx*>(smem_tma);      // [TB][LDB]
@@ -861,9 +864,8 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   cplx* part = wc + TB;                              // [NP][LDP]
   cplx* red = part + NP * LDP;                       // [32]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
+  int* sw = reinterpret_cast<int*>(bar + 1);         // [2] chain and sweep of the ticket just taken (-1: none left)
   const int tid = threadIdx.x;
-  cplx* AB = g.AB + (size_t)chain * n * LD;
-  int* prog = g.prog + (size_t)chain * n;
   if (tid == 0) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -874,7 +876,26 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
     const bool l0 = tid == NC;
     bool store_pending = false, publish_pending = false;
     int pub_s = 0, pub_v = 0;
-    for (int s = p; s < n - 1; s += g.P) {
+    const bool spare = (int)blockIdx.x >= 2 * g.B;
+    int home = (spare ? (int)blockIdx.x - 2 * g.B : (int)blockIdx.x / 2) % g.B;   // neighbouring CTAs share a chain
+    const int hop = 1 + (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)g.B);      // where to look once home is exhausted
+    for (;;) {
+      int s = -1, chain = 0;
+      if (l0) {
+        for (int tries = 0; tries <= g.B; ++tries) {     // home first, then every chain starting from a CTA-specific one
+          int c = (tries == 0) ? home : (home + hop + tries - 1) % g.B;
+          if (!g.mask.on(c)) continue;
+          const int v = atomicAdd(g.next + c, 1);
+          if (v < n - 1) { s = v; chain = c; break; }
+        }
+        sw[0] = chain; sw[1] = s;
+      }
+      s = __shfl_sync(0xffffffffu, s, 0);
+      chain = __shfl_sync(0xffffffffu, chain, 0);
+      if (s < 0) { hbar_arrive<NC>(2); return; }       // nothing left anywhere
+      home = spare ? (chain + g.stride) % g.B : chain;
+      cplx* AB = g.AB + (size_t)chain * n * LD;
+      int* prog = g.prog + (size_t)chain * n;
       int k = 0, r0 = s + 1, lcar = 0;
       while (true) {
         const int ln = min(TB, n - r0);
@@ -957,7 +978,6 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
       store_pending = false;
       publish_pending = false;
     }
-    return;
   }
 
   // ================= compute threads =================
@@ -965,8 +985,8 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
   const int soff = cj * LDB + ri;
   const int goff = cj * (LD - 1) + ri;
-  cplx* V = g.V + (size_t)chain * n * n;
-  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
+  cplx* AB = nullptr;
+#define VCOL (g.V + ((size_t)sw[0] * n + s) * n)      /* reflector column of this sweep (rarely needed: not kept in registers) */
   const cplx zero = make_double2(0.0, 0.0);
 #ifdef DWHMC_CHASE_PROF                              // phase clocks of CTA 0 (experiments): accumulators in shared memory
   __shared__ long long tph[8];
@@ -979,15 +999,22 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
 #define PH(i) do { } while (0)
 #endif
-  for (int s = p; s < n - 1; s += g.P) {
-    int k = 0, r0 = s + 1;
+  for (;;) {
+    int s = 0, k = 0, r0 = 0;
     cplx taup = zero;
     int lcar = 0;                                    // rows of the carried block in Bc
     while (true) {
-      const int ln = min(TB, n - r0);
       if (prof) tlast = clock64();
       hbar_sync<NC>(2);                                  // sweep s-1 two steps ahead, carried block landed and patched
       PH(7);
+      if (k == 0) {                                  // a new sweep: which one, of which chain
+        s = sw[1];
+        if (s < 0) break;
+        const int chain = sw[0];
+        r0 = s + 1;
+        AB = g.AB + (size_t)chain * n * LD;
+      }
+      const int ln = min(TB, n - r0);
       double nrm2 = 0.0;                               // |x[1:]|^2, summed where x is produced
       if (k > 0) {
         mbar_wait(bar, ephase);                      // completed already: makes the bulk copy visible to this thread
@@ -1030,20 +1057,23 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           cfms(a, cmul(taup, us[i]), cconj(vp[j]));
           stg2(AB + (size_t)(r0 - TB + j) * LD + (TB + i - j), a);
         }
-        for (int i = tid; i < ln; i += NC) V[(size_t)s * n + r0 + i] = zero;
+        for (int i = tid; i < ln; i += NC) VCOL[r0 + i] = zero;
         break;
       }
       // ---- prefetch the lower triangle of the diagonal block into registers
       cplx* baseD = AB + (size_t)r0 * LD + goff;
       cplx dreg[RB][CB];
+      auto prefetch_D = [&]() {
 #pragma unroll
-      for (int c = 0; c < CB; ++c)
+        for (int c = 0; c < CB; ++c)
 #pragma unroll
-        for (int q = 0; q < RB; ++q) {
-          const int i = ri + q * TR, j = cj + c * TC;
-          if (q * TR + TR - 1 < c * TC) continue;      // sub-block wholly above the diagonal: never referenced
-          dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
-        }
+          for (int q = 0; q < RB; ++q) {
+            const int i = ri + q * TR, j = cj + c * TC;
+            if (q * TR + TR - 1 < c * TC) continue;    // sub-block wholly above the diagonal: never referenced
+            dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
+          }
+      };
+      prefetch_D();
       // ---- A. column to annihilate
       if (k == 0) {
         for (int i = tid; i < ln; i += NC) {
@@ -1078,8 +1108,8 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         csync<NC>();
       }
       PH(2);
-      for (int i = tid; i < ln; i += NC) V[(size_t)s * n + r0 + i] = vs[i];
-      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
+      for (int i = tid; i < ln; i += NC) VCOL[r0 + i] = vs[i];
+      if (tid == 0) g.tau2[((size_t)sw[0] * n + s) * g.KT + k] = tau;
       cplx vr[RB];
 #pragma unroll
       for (int q = 0; q < RB; ++q) vr[q] = (ri + q * TR < ln) ? vs[ri + q * TR] : zero;
@@ -1249,16 +1279,18 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
       r0 = r1;
       ++k;
     }
+    if (s < 0) break;
     hbar_arrive<NC>(4);
   }
   if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
 #undef PH
 #undef JV
+#undef VCOL
 }
 
 template <int TB, int TR, int TC>
 constexpr size_t chase_tma_smem() {
-  return sizeof(cplx) * ((size_t)TB * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * (TB + 1) + 32) + 16;
+  return sizeof(cplx) * ((size_t)TB * TB + 6 * TB + (size_t)((TR > TC) ? TR : TC) * (TB + 1) + 32) + 32;
 }
 
 // Tensor map of the band storage of all chains as the skewed view T[chain][c][r] = AB[chain][c LD + (r - c)]
@@ -1676,7 +1708,7 @@ static cudaEvent_t g_chase_done[64] = {};
 
 // launch helper: P persistent CTAs per chain, all co-resident (cooperative launch), chains in slices if needed
 template <class Launch>
-static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthreads, size_t smem, Launch launch) {
+static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthreads, size_t smem, bool tickets, Launch launch) {
   const int n = h->n, B = h->B, bw = h->band_b;
   int per_sm = 0;
   DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
@@ -1684,7 +1716,8 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
   if (cap < 1) { h->err = "dw_band_chase: kernel does not fit"; return DWHMC_E_CUDA; }
   int P = std::max(1, std::min(4, cap / B));
   if (const char* e = getenv("DWHMC_BAND_P")) P = std::max(1, std::min(atoi(e), cap));
-  const int per_launch = std::max(1, cap / P);                    // chains per launch
+  // ticket kernel: one launch over all chains with every CTA that fits (at most 4 per chain)
+  const int per_launch = tickets ? B : std::max(1, cap / P);      // chains per launch
   std::lock_guard<std::mutex> lock(g_chase_mutex);
   cudaEvent_t& done = g_chase_done[h->device & 63];
   if (!done) DW_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
@@ -1694,12 +1727,21 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
     ChaseArgs a;
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
     a.n = n; a.b = bw; a.LD = h->band_LD; a.KT = h->band_KT; a.P = P; a.c0 = c0; a.mask = mask;
+    a.next = h->band_prog + (size_t)n * B; a.B = B; a.stride = 1;
     static long long* clk_dev = nullptr;
     static const bool want_clk = getenv("DWHMC_BAND_CLK") != nullptr;
     if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
     a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
     const int nch = std::min(per_launch, B - c0);
-    DW_TRY(launch(a, nch * P));
+    int nctas = nch * P;
+    if (tickets) {
+      nctas = std::min(cap, 4 * B);
+      if (const char* e = getenv("DWHMC_BAND_CTAS")) nctas = std::max(1, std::min(atoi(e), cap));
+      auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+      a.stride = std::max(1, nctas - 2 * B);                     // spare CTAs visit every chain in turn
+      while (gcd(a.stride, B) != 1) ++a.stride;
+    }
+    DW_TRY(launch(a, nctas));
     h->launches++;
     if (a.clk) {
       long long c[8];
@@ -1732,7 +1774,7 @@ static int chase_tma_dispatch(Handle* h, Mask mask) {
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_b), TB - pw * (npiece - 1)));
     h->band_tmap_set = true;
   }
-  return chase_launch_loop(h, mask, kern, nthreads, smem, [&](ChaseArgs& a, int ctas) -> int {
+  return chase_launch_loop(h, mask, kern, nthreads, smem, HELPER, [&](ChaseArgs& a, int ctas) -> int {
     void* targs_h[] = {&a, h->band_tmap_a, h->band_tmap_b};
     void* targs[] = {&a, h->band_tmap};
     DW_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(nthreads), HELPER ? targs_h : targs, smem, h->stream));
@@ -1747,7 +1789,7 @@ bool dw_band_has_tma_kernel(int bw) { return bw >= 28 && bw <= 100 && (bw - 28) 
 // h->A (band) -> h->d, h->e, h->V (reflectors, column s = sweep s), h->band_tau
 int dw_band_chase(Handle* h, Mask mask) {
   const int n = h->n, B = h->B, bw = h->band_b;
-  DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * (size_t)n * B, h->stream));
+  DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * ((size_t)n + 1) * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
   // DWHMC_BAND_HELPER=0: the variant without the helper warp (every thread waits on the memory system in turn).
@@ -1778,7 +1820,7 @@ int dw_band_chase(Handle* h, Mask mask) {
       DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       attr_set[h->device & 63] = true;
     }
-    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, CT, smem, [&](ChaseArgs& a, int ctas) -> int {
+    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, CT, smem, false, [&](ChaseArgs& a, int ctas) -> int {
       void* args[] = {&a};
       DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctas), dim3(CT), args, smem, h->stream));
       return DWHMC_OK;

@@ -129,7 +129,7 @@ struct Handle {
   std::vector<int> band_wave_blk, band_wave_start;   // blocks sorted into wavefronts of independent blocks
   int* band_wave_dev = nullptr;
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
-  int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase)
+  int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
   cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
   cplx* band_VT = nullptr;      // device [nblk*32*128*B]: V T per block (fused back-transformation), or null
