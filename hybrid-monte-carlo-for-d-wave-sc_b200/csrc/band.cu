@@ -464,6 +464,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory writes only (the block a tensor store is about to read): does not wait for global stores in flight
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int TB, int TR, int TC, int RB, int CB>
 __global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmap) {
@@ -985,9 +987,31 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
   const int soff = cj * LDB + ri;
   const int goff = cj * (LD - 1) + ri;
-  cplx* AB = nullptr;
-#define VCOL (g.V + ((size_t)sw[0] * n + s) * n)      /* reflector column of this sweep (rarely needed: not kept in registers) */
   const cplx zero = make_double2(0.0, 0.0);
+  cplx* AB = nullptr;
+  // partial sums are added up by four neighbouring lanes per row / column (fixed order), then two shuffles
+  static_assert(NC >= 4 * TB, "four lanes per entry");
+  const int ei = tid >> 2, esl = tid & 3;
+  auto sum4 = [&](int col, int nq, bool valid) -> cplx {     // sum_q part[q][col], q < nq; result in all four lanes
+    cplx a = zero;
+    if (valid)
+      for (int q = esl; q < nq; q += 4) a = cadd(a, part[q * LDP + col]);
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, 1); a.y += __shfl_xor_sync(0xffffffffu, a.y, 1);
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, 2); a.y += __shfl_xor_sync(0xffffffffu, a.y, 2);
+    return a;
+  };
+  auto red_sum = [&]() -> cplx {                             // sum of the per-warp partials, four independent chains
+    cplx a0 = zero, a1 = zero, a2 = zero, a3 = zero;
+#pragma unroll
+    for (int w = 0; w < NC / 32; w += 4) {
+      a0 = cadd(a0, red[w]);
+      if (w + 1 < NC / 32) a1 = cadd(a1, red[w + 1]);
+      if (w + 2 < NC / 32) a2 = cadd(a2, red[w + 2]);
+      if (w + 3 < NC / 32) a3 = cadd(a3, red[w + 3]);
+    }
+    return cadd(cadd(a0, a1), cadd(a2, a3));
+  };
+#define VCOL (g.V + ((size_t)sw[0] * n + s) * n)      /* reflector column of this sweep (rarely needed: not kept in registers) */
 #ifdef DWHMC_CHASE_PROF                              // phase clocks of CTA 0 (experiments): accumulators in shared memory
   __shared__ long long tph[8];
   long long tlast = 0;
@@ -1035,17 +1059,17 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
         }
         csync<NC>();
-        for (int i = tid; i < lcar; i += NC) {
-          cplx u = part[i];
-#pragma unroll 5
-          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * LDP + i]);
-          us[i] = u;
-          // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
-          const cplx t = cmul(taup, u);
-          tu[i] = t;
-          const cplx x = csub(Bc[i], t);
-          xs[i] = x;
-          if (i > 0) nrm2 += x.x * x.x + x.y * x.y;
+        {
+          const cplx u = sum4(ei, TC, ei < lcar);
+          if (esl == 0 && ei < lcar) {
+            us[ei] = u;
+            // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
+            const cplx t = cmul(taup, u);
+            tu[ei] = t;
+            const cplx x = csub(Bc[ei], t);
+            xs[ei] = x;
+            if (ei > 0) nrm2 += x.x * x.x + x.y * x.y;
+          }
         }
       }
       PH(0);
@@ -1083,15 +1107,13 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         }
       }
       nrm2 = warp_sum(make_double2(nrm2, 0.0)).x;
-      if ((tid & 31) == 0) red[tid >> 5].x = nrm2;
+      if ((tid & 31) == 0) red[tid >> 5] = make_double2(nrm2, 0.0);
       PH(5);
       csync<NC>();
       // ---- B. reflector (LAPACK zlarfg; every thread computes tau, beta and the scale)
       cplx tau; double beta;
       {
-        double nrm = 0.0;
-#pragma unroll
-        for (int w = 0; w < NC / 32; ++w) nrm += red[w].x;
+        const double nrm = red_sum().x;
         const cplx alpha = xs[0];
         cplx scale;
         if (nrm == 0.0 && alpha.y == 0.0) {
@@ -1100,9 +1122,10 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           scale = zero;
         } else {
           beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm), alpha.x);
-          tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-          const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
-          scale = make_double2(dr / den, -di / den);
+          const double dr = alpha.x - beta, di = alpha.y;
+          const double ibeta = 1.0 / beta, iden = 1.0 / (dr * dr + di * di);   // two independent divisions
+          tau = make_double2(-dr * ibeta, -di * ibeta);
+          scale = make_double2(dr * iden, -di * iden);
         }
         for (int i = tid; i < ln; i += NC) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
         csync<NC>();
@@ -1138,12 +1161,13 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         csync<NC>();
         PH(1);
         const cplx ctau = cconj(tau);
-        for (int j = tid; j < TB; j += NC) {
-          cplx z = part[j], c = part[TB];
-#pragma unroll 5
-          for (int q = 1; q < TR; ++q) { z = cadd(z, part[q * LDP + j]); c = cadd(c, part[q * LDP + TB]); }
-          cfms(z, c, cconj(vp[j]));
-          wc[j] = cmul(ctau, z);
+        {
+          cplx z = sum4(ei, TR, ei < TB);
+          const cplx c = sum4(TB, TR, true);
+          if (esl == 0 && ei < TB) {
+            cfms(z, c, cconj(vp[ei]));
+            wc[ei] = cmul(ctau, z);
+          }
         }
         csync<NC>();
         {
@@ -1168,7 +1192,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
               }
             }
             if ((cc & 1) == 1 || cc == CB - 1) {
-              fence_async();                            // generic-proxy writes of Bc -> visible to the bulk engine
+              fence_async_smem();                       // generic-proxy writes of Bc -> visible to the bulk engine
               hbar_arrive<NC>(5 + cc / 2);              // the helper writes this piece back
             }
           }
@@ -1198,11 +1222,9 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
         }
         csync<NC>();
-        for (int i = tid; i < ln; i += NC) {
-          cplx wv = part[i];
-#pragma unroll 5
-          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * LDP + i]);
-          xs[i] = wv;
+        {
+          const cplx wv = sum4(ei, TC, ei < ln);
+          if (esl == 0 && ei < ln) xs[ei] = wv;
         }
         csync<NC>();
         // column part: sum_{i > j} conj(D[i,j]) v[i]
@@ -1220,13 +1242,13 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         }
         csync<NC>();
         cplx dot = zero;
-        for (int i = tid; i < ln; i += NC) {
-          cplx wv = xs[i];
-#pragma unroll 5
-          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * LDP + i]);
-          wv = cmul(tau, wv);
-          xs[i] = wv;
-          cfmac(dot, wv, vs[i]);
+        {
+          cplx wv = sum4(ei, TR, ei < ln);
+          if (esl == 0 && ei < ln) {
+            wv = cmul(tau, cadd(xs[ei], wv));
+            xs[ei] = wv;
+            cfmac(dot, wv, vs[ei]);
+          }
         }
         dot = warp_sum(dot);
         if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
@@ -1234,10 +1256,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
       }
       cplx alpha;                                      // w = y + alpha v, formed where it is used
       {
-        cplx dsum = zero;
-#pragma unroll
-        for (int w = 0; w < NC / 32; ++w) dsum = cadd(dsum, red[w]);
-        alpha = cmul(tau, dsum);
+        alpha = cmul(tau, red_sum());
         alpha.x *= -0.5; alpha.y *= -0.5;
       }
       PH(4);
