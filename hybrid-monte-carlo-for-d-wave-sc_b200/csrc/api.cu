@@ -118,7 +118,13 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device);
   auto fail = [&](int rc) { g_create_err = h->err; dwhmc_destroy(hs); return rc; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DWHMC_E_CUDA); }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
+  {
+    // the main stream runs at the high priority: work forked to the low-priority side streams (T factors beside the
+    // D&C stage) only fills the SMs the main stream leaves free
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { h->err = "stream create failed"; return fail(DWHMC_E_CUDA); }
+  }
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaEventCreate(&h->ev_begin);

@@ -907,8 +907,10 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
             while (ld_acquire(prog + s - 1) < need) __nanosleep(20);
           }
           if (k > 0) {
+            // the corner element is fetched while the last piece of the block is still landing
+            const cplx corner = (lcar == TB) ? ldg2(AB + (size_t)(r0 - 1) * LD + TB) : make_double2(0.0, 0.0);
             mbar_wait(bar, ephase);
-            if (lcar == TB) Bc[(TB - 1) * LDB + TB - 1] = ldg2(AB + (size_t)(r0 - 1) * LD + TB);
+            if (lcar == TB) Bc[(TB - 1) * LDB + TB - 1] = corner;
           }
         }
         if (k > 0) ephase ^= 1;
