@@ -31,6 +31,10 @@
 #include "gemm_dmma.cuh"
 #include "internal.h"
 
+#ifndef DWHMC_CHASE_PCC
+#define DWHMC_CHASE_PCC 2
+#endif
+
 namespace {
 
 constexpr int CT = 512;             // threads per CTA of the chase kernel
@@ -833,6 +837,8 @@ template <int NC> __device__ __forceinline__ void larfg_block_c(const cplx* xs, 
 }
 
 __host__ __device__ constexpr int chase_nc(int tr, int tc) { return (tr * tc + 31) / 32 * 32; }
+// thread-columns per piece of the carried block (helper-warp kernel)
+__host__ __device__ constexpr int chase_pcc(int cb) { return DWHMC_CHASE_PCC; }
 
 template <int TB, int TR, int TC, int RB, int CB>
 __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmapA,
@@ -841,11 +847,14 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   static_assert(TR * RB == TB && TC * CB >= TB && TC * (CB - 1) < TB && TB <= NC && NC + 32 <= 512, "cover, at most 16 warps");
   constexpr bool XC = TC * CB == TB;             // exact column cover; otherwise the last column of a thread may not exist
 #define JV(cc) (XC || (cc) < CB - 1 || cj + (cc) * TC < TB)
-  // The carried block travels in column pieces of two thread-columns each (2 TC matrix columns; the last piece takes
+  // The carried block travels in column pieces of PCC thread-columns each (PCC TC matrix columns; the last piece takes
   // the rest): a piece is written back as soon as it is updated, and its place is refilled from the next block as
-  // soon as the write-back has read it.  tmapA: boxes of 2 TC columns, tmapB: box of the last piece.
-  constexpr int NPIECE = (CB + 1) / 2;
-  constexpr int PW = 2 * TC;
+  // soon as the write-back has read it.  tmapA: boxes of PCC TC columns, tmapB: box of the last piece.
+  constexpr int PCC = chase_pcc(CB);
+  constexpr int NPIECE = (CB + PCC - 1) / PCC;
+  constexpr int PW = PCC * TC;
+  static_assert(5 + NPIECE <= 16, "named barriers");
+  static_assert(NPIECE == 1 || (PW * LDB * sizeof(cplx)) % 128 == 0, "tensor copies need 128-byte aligned shared memory");
   constexpr int LDB = TB;        // dense box layout of the tensor copies
   constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
   constexpr int LD = 2 * TB;
@@ -1193,9 +1202,9 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
                 }
               }
             }
-            if ((cc & 1) == 1 || cc == CB - 1) {
+            if ((cc + 1) % PCC == 0 || cc == CB - 1) {
               fence_async_smem();                       // generic-proxy writes of Bc -> visible to the bulk engine
-              hbar_arrive<NC>(5 + cc / 2);              // the helper writes this piece back
+              hbar_arrive<NC>(5 + cc / PCC);            // the helper writes this piece back
             }
           }
         }
@@ -1789,7 +1798,7 @@ static int chase_tma_dispatch(Handle* h, Mask mask) {
   }
   static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
   if (!h->band_tmap_set) {
-    constexpr int npiece = (CB + 1) / 2, pw = 2 * TC;      // column pieces of the helper-warp kernel
+    constexpr int pcc = chase_pcc(CB), npiece = (CB + pcc - 1) / pcc, pw = pcc * TC;   // column pieces of the helper-warp kernel
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap), TB));
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_a), std::min(pw, TB)));
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_b), TB - pw * (npiece - 1)));
