@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   constexpr int NPIECE = (CB + PCC - 1) / PCC;
   constexpr int PW = PCC * TC;
   static_assert(5 + NPIECE <= 16, "named barriers");
-  static_assert(NPIECE == 1 || (PW * LDB * sizeof(cplx)) % 128 == 0, "tensor copies need 128-byte aligned shared memory");
+  static_assert(NPIECE == 1 || (PW * TB * sizeof(cplx)) % 128 == 0, "tensor copies need 128-byte aligned shared memory");
   constexpr int LDB = TB;        // dense box layout of the tensor copies
   constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
   constexpr int LD = 2 * TB;
