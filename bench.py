@@ -34,7 +34,7 @@ METRIC = "HMC trajectories/sec at L=24 (disordered T-scan shard, Nt=6)"
 # dram__bytes_read.sum + dram__bytes_write.sum vs the algorithmic bytes of that launch (profiles/r01e_*)
 NCU_HEMV = {"dram_bytes": 691.7e6, "algorithmic_bytes": 678.9e6}
 # one ncu --set full capture of the bulge-chase kernel (64 chains, n = 1152, b = 100): DRAM read + write per launch
-NCU_CHASE = {"dram_bytes": 35.96e9 + 59.92e9}
+NCU_CHASE = {"dram_bytes": 37.07e9 + 60.04e9}
 
 
 def temperatures(n_points=32):
@@ -309,8 +309,8 @@ def run_ours(args):
         dom = {"kernel": "chase_tmah_kernel (band -> tridiagonal bulge chase; one cooperative launch per batched eigensolve, "
                          "one persistent CTA per SM: 15 compute warps + 1 helper warp for polls, TMA copies and publishes)",
                "traffic": NCU_CHASE["dram_bytes"],
-               "traffic_note": "ncu --set full (profiles/r01h_chase_tmah_full.ncu-rep): dram read 36.0 GB + write 59.9 GB per launch; "
-                               "below the algorithmic count because consecutive sweeps re-read each other's blocks from L2 (69 % hit)",
+               "traffic_note": "ncu --set full (profiles/r01h_chase_tmah_full.ncu-rep): dram read 37.1 GB + write 60.0 GB per launch; "
+                               "below the algorithmic count because consecutive sweeps re-read each other's blocks from L2 (70 % hit)",
                "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_us": dom_ms * 1e3 / n_solves,
                "share_of_eigensolve": dom_ms / eig_ms}
     else:
