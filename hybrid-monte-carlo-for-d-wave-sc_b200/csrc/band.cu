@@ -6,12 +6,15 @@
 // stage of a two-stage eigensolver is free.  This file holds the rest:
 //   assemble_band   H straight into lower band storage  AB[d + j LD] = H[j + d, j], LD = 2b
 //   chase           band -> real tridiagonal by Householder bulge chasing (Lang's algorithm):
-//                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; a persistent CTA per sweep
-//                   in flight, sweeps of a chain pipelined through release/acquire progress counters
-//                   (two steps apart in chase_tma_kernel, three in the generic chase_kernel); the
-//                   block pushed out by a step stays in shared memory for the next one (3 b^2
-//                   elements of global traffic per step).  chase_tma_kernel<b, ...> (compile-time b)
-//                   moves the blocks with TMA tensor copies; chase_kernel handles any b <= 101.
+//                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; persistent CTAs, one sweep
+//                   each at a time, sweeps of a chain pipelined through release/acquire progress
+//                   counters (two steps apart in the TMA kernels, three in the generic chase_kernel);
+//                   the block pushed out by a step stays in shared memory for the next one (3 b^2
+//                   elements of global traffic per step).  chase_tmah_kernel<b, ...> (compile-time b,
+//                   the default): TMA tensor copies in column pieces, a helper warp for everything that
+//                   waits on the memory system, sweeps handed out by ticket counters to one CTA per SM;
+//                   chase_tma_kernel<b, ...>: its predecessor without helper warp (DWHMC_BAND_HELPER=0);
+//                   chase_kernel handles any b <= 101.
 //   tfactor + back-transformation   U = Q2 Z: reflectors of g consecutive sweeps at the same step
 //                   form one staircase block reflector; band_apply_kernel applies a wavefront of
 //                   independent blocks per launch on the FP64 tensor cores (fallback: three DMMA
