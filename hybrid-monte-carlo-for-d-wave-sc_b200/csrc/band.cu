@@ -959,19 +959,14 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
             hbar_sync<NC>(5 + pc);                     // piece pc of the carried block updated in shared memory
             if (l0) {
               store_piece(pc);
-              if (l2 > 0 && pc >= 1) {
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // piece pc-1 has been read
-                if (pc == 1) { fence_async(); mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx))); }
-                load_piece(pc - 1);
+              if (l2 > 0) {                            // refill the piece as soon as its write-back has read it
+                bulk_wait_read();
+                if (pc == 0) { fence_async(); mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx))); }
+                load_piece(pc);
               }
             }
           }
           store_pending = true;
-          if (l0 && l2 > 0) {
-            bulk_wait_read();
-            if (NPIECE == 1) { fence_async(); mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx))); }
-            load_piece(NPIECE - 1);
-          }
         } else if (l0 && l2 > 0) {
           fence_async();
           mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));
