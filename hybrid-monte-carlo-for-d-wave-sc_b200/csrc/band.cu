@@ -141,6 +141,7 @@ struct ChaseArgs {
   cplx* AB; cplx* V; cplx* tau2; int* prog;
   int n, b, LD, KT, P, c0;       // c0: first chain of this launch
   int* next; int B, stride;      // helper-warp kernel: per-chain sweep tickets, chains, rotation stride of the spare CTAs
+  int nsweep;                    // sweeps handed out by tickets (the rest is left to chase_tail_kernel)
   Mask mask;
   long long* clk;                // optional [8] phase clock accumulators of CTA 0 (profiling experiments)
 };
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           int c = (tries == 0) ? home : (home + hop + tries - 1) % g.B;
           if (!g.mask.on(c)) continue;
           const int v = atomicAdd(g.next + c, 1);
-          if (v < n - 1) { s = v; chain = c; break; }
+          if (v < g.nsweep) { s = v; chain = c; break; }
         }
         sw[0] = chain; sw[1] = s;
       }
@@ -1346,6 +1347,106 @@ static int make_band_tensor_map(Handle* h, CUtensorMap* out, int box_cols) {
   return DWHMC_OK;
 }
 
+// ---- the last b sweeps: a dense (b+1) x (b+1) Hermitian block, one CTA per chain -------------------------
+// Sweeps s >= n-1-b have a single step each and would run strictly one after the other through the progress
+// counters.  Here the trailing block is copied to shared memory (full storage) and tridiagonalised in place with
+// the same reflector and update formulas as the chase; reflectors and tau go where the chase would have put them.
+constexpr int TAIL_T = 512;
+__global__ void __launch_bounds__(TAIL_T, 1) chase_tail_kernel(ChaseArgs g) {
+  const int chain = blockIdx.x;
+  if (!g.mask.on(chain)) return;
+  extern __shared__ __align__(16) unsigned char smem_tail[];
+  const int n = g.n, b = g.b, LD = g.LD;
+  const int m0 = b + 1, ldf = m0 | 1;                // odd leading dimension
+  cplx* F = reinterpret_cast<cplx*>(smem_tail);      // [m0][ldf] column-major, both triangles
+  cplx* vs = F + (size_t)ldf * m0;                   // [m0]
+  cplx* ys = vs + m0;                                // [m0]
+  cplx* red = ys + m0;                               // [32]
+  const int tid = threadIdx.x;
+  const int s0 = n - 1 - b;                          // global index of local row / column 0
+  cplx* AB = g.AB + (size_t)chain * n * LD;
+  cplx* V = g.V + (size_t)chain * n * n;
+  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
+  const cplx zero = make_double2(0.0, 0.0);
+  for (int idx = tid; idx < m0 * m0; idx += TAIL_T) {
+    const int r = idx % m0, c = idx / m0;
+    if (r >= c) {
+      cplx a = ldg2(AB + (size_t)(s0 + c) * LD + (r - c));
+      if (r == c) a.y = 0.0;
+      F[(size_t)c * ldf + r] = a;
+      if (r > c) F[(size_t)r * ldf + c] = cconj(a);
+    }
+  }
+  __syncthreads();
+  const int ei = tid >> 2, esl = tid & 3;            // four lanes per row of the matrix-vector product
+  for (int j = 0; j < b; ++j) {
+    const int m = b - j;                             // order of the trailing block A22 = F[j+1.., j+1..]
+    const int s = s0 + j;
+    const cplx* x = F + (size_t)j * ldf + j + 1;     // column to annihilate
+    // reflector (zlarfg)
+    double nrm2 = 0.0;
+    for (int i = 1 + tid; i < m; i += TAIL_T) { const cplx a = x[i]; nrm2 += a.x * a.x + a.y * a.y; }
+    const cplx nr = block_sum(make_double2(nrm2, 0.0), red);
+    const cplx alpha0 = x[0];
+    cplx tau, scale; double beta;
+    if (nr.x == 0.0 && alpha0.y == 0.0) {
+      beta = alpha0.x; tau = zero; scale = zero;
+    } else {
+      beta = -copysign(sqrt(alpha0.x * alpha0.x + alpha0.y * alpha0.y + nr.x), alpha0.x);
+      const double dr = alpha0.x - beta, di = alpha0.y;
+      const double ibeta = 1.0 / beta, iden = 1.0 / (dr * dr + di * di);
+      tau = make_double2(-dr * ibeta, -di * ibeta);
+      scale = make_double2(dr * iden, -di * iden);
+    }
+    for (int i = tid; i < m; i += TAIL_T) {
+      const cplx v = (i == 0) ? make_double2(1.0, 0.0) : cmul(x[i], scale);
+      vs[i] = v;
+      V[(size_t)s * n + s + 1 + i] = v;
+    }
+    if (tid == 0) tau2[(size_t)s * g.KT] = tau;
+    __syncthreads();
+    // y = tau A22 v
+    {
+      cplx acc = zero;
+      if (ei < m) {
+        const cplx* row = F + (size_t)(j + 1) * ldf + (j + 1 + ei);
+        for (int c = esl; c < m; c += 4) cfma(acc, row[(size_t)c * ldf], vs[c]);
+      }
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+      cplx dot = zero;
+      if (esl == 0 && ei < m) {
+        const cplx wv = cmul(tau, acc);
+        ys[ei] = wv;
+        cfmac(dot, wv, vs[ei]);
+      }
+      dot = block_sum(dot, red);
+      cplx al = cmul(tau, dot);
+      al.x *= -0.5; al.y *= -0.5;
+      // A22 -= v w^H + w v^H with w = y + alpha v (both triangles are kept)
+      for (int idx = tid; idx < m * m; idx += TAIL_T) {
+        const int r = idx % m, c = idx / m;
+        cplx wr = ys[r], wc = ys[c];
+        const cplx vr = vs[r], vc = vs[c];
+        cfma(wr, al, vr);
+        cfma(wc, al, vc);
+        cplx a = F[(size_t)(j + 1 + c) * ldf + (j + 1 + r)];
+        cfms(a, vr, cconj(wc));
+        cfms(a, wr, cconj(vc));
+        if (r == c) a.y = 0.0;
+        F[(size_t)(j + 1 + c) * ldf + (j + 1 + r)] = a;
+      }
+    }
+    if (tid == 0) F[(size_t)j * ldf + j + 1] = make_double2(beta, 0.0);
+    __syncthreads();
+  }
+  // diagonal and sub-diagonal back to the band storage (all that band_de_kernel reads)
+  for (int c = tid; c < m0; c += TAIL_T) {
+    stg2(AB + (size_t)(s0 + c) * LD, make_double2(F[(size_t)c * ldf + c].x, 0.0));
+    if (c + 1 < m0) stg2(AB + (size_t)(s0 + c) * LD + 1, make_double2(F[(size_t)c * ldf + c + 1].x, 0.0));
+  }
+}
+
 __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restrict__ d, double* __restrict__ e, int n,
                                int LD, Mask mask) {
   const int b = blockIdx.y;
@@ -1756,6 +1857,9 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
     a.n = n; a.b = bw; a.LD = h->band_LD; a.KT = h->band_KT; a.P = P; a.c0 = c0; a.mask = mask;
     a.next = h->band_prog + (size_t)n * B; a.B = B; a.stride = 1;
+    static const bool no_tail = getenv("DWHMC_BAND_NOTAIL") != nullptr;
+    const bool tail = tickets && !no_tail && n - 1 - bw >= 1;
+    a.nsweep = tail ? n - 1 - bw : n - 1;
     static long long* clk_dev = nullptr;
     static const bool want_clk = getenv("DWHMC_BAND_CLK") != nullptr;
     if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
@@ -1771,6 +1875,17 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
     }
     DW_TRY(launch(a, nctas));
     h->launches++;
+    if (tail) {
+      const size_t tsm = sizeof(cplx) * ((size_t)((bw + 1) | 1) * (bw + 1) + 2 * (size_t)(bw + 1) + 32);
+      static bool tattr[64] = {false};
+      if (!tattr[h->device & 63]) {
+        DW_CUDA(h, cudaFuncSetAttribute(chase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        tattr[h->device & 63] = true;
+      }
+      chase_tail_kernel<<<B, TAIL_T, tsm, h->stream>>>(a);
+      DW_LAUNCH_CHECK(h);
+      h->launches++;
+    }
     if (a.clk) {
       long long c[8];
       cudaStreamSynchronize(h->stream);
