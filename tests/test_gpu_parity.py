@@ -752,3 +752,26 @@ def test_default_route_is_band_where_a_chase_kernel_exists(dw):
         cb = dw.ChainBatch(1, Lx, Ly)
         assert cb.band_halfwidth() == expect, (L, cb.band_halfwidth())
         cb.close()
+
+
+@pytest.mark.parametrize("switch", ["DWHMC_BAND_HELPER=0", "DWHMC_BAND_NOTAIL=1", "DWHMC_BAND_GENERIC=1"])
+def test_chase_fallback_kernels(switch):
+    """The bulge-chase variants behind the (process-wide, read-once) switches -- the TMA kernel without helper warp and
+    with static sweep assignment, the helper kernel without the dense tail kernel, the generic LSU kernel -- against
+    LAPACK, each in a process of its own: eigenvalues, residual and unitarity of two chains at L = 8 (b = 36) and of a
+    rectangular lattice whose half-bandwidth is rounded up (5 x 13: 24 -> 28)."""
+    import re
+    import subprocess
+    import sys
+    key, val = switch.split("=")
+    env = dict(os.environ, **{key: val})
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for args in (["8", "3"], ["5x13", "2"]):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "band_check.py")] + args, env=env,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        rows = re.findall(r"chain \d+ E err (\S+) res (\S+) orth (\S+)", out.stdout)
+        assert len(rows) == 2, out.stdout[-2000:]
+        for err, res, orth in rows:
+            assert float(err) <= 1e-12 and float(res) <= 1e-12 and float(orth) <= 1e-12, (switch, args, rows)
+        assert re.search(r"route half-bandwidth (\d+)", out.stdout).group(1) != "0"

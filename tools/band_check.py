@@ -1,13 +1,15 @@
-"""Band-route check on the GPU box: python tools/band_check.py L B"""
+"""Band-route check on the GPU box: python tools/band_check.py L B   (L: side, or LxxLy)"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "hybrid-monte-carlo-for-d-wave-sc_b200"))
 import dwhmc
-L, B = int(sys.argv[1]), int(sys.argv[2])
-N, n = L * L, 2 * L * L
+Lx, Ly = (int(v) for v in sys.argv[1].split("x")) if "x" in sys.argv[1] else (int(sys.argv[1]),) * 2
+B = int(sys.argv[2])
+N, n = Lx * Ly, 2 * Lx * Ly
 rng = np.random.default_rng(0)
-cb = dwhmc.ChainBatch(B, L, L)
+cb = dwhmc.ChainBatch(B, Lx, Ly)
+print("route half-bandwidth", cb.band_halfwidth())
 cb.set_params(1.0, -0.35, -1.08, np.logspace(-1, 2, B), 0.8, 1.0)
 w = np.zeros((B, N))
 for b in range(B):
