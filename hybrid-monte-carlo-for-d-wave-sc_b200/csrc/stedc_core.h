@@ -62,15 +62,19 @@ DW_HD int tql_implicit(int n, double* d, double* e, Rot& rot) {
         for (i = m - 1; i >= l; --i) {
           double f = s * e[i];
           double b = c * e[i];
-          r = hypot(f, g);
+          // sqrt(f^2 + g^2) directly where that cannot over- or underflow (hypot's scaling costs about as much as the
+          // rest of the rotation, and this recurrence is one long dependency chain per leaf)
+          const double r2 = f * f + g * g;
+          r = (r2 > 1e-280 && r2 < 1e280) ? sqrt(r2) : hypot(f, g);
           e[i + 1] = r;
           if (r == 0.0) {
             d[i + 1] -= p;
             e[m] = 0.0;
             break;
           }
-          s = f / r;
-          c = g / r;
+          const double rinv = 1.0 / r;
+          s = f * rinv;
+          c = g * rinv;
           g = d[i + 1] - p;
           r = (d[i] - g) * s + 2.0 * c * b;
           p = s * r;
