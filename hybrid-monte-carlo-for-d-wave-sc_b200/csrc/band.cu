@@ -809,37 +809,6 @@ template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
   __threadfence_block();
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NC + 32) : "memory");
 }
-template <int NC> __device__ __forceinline__ cplx block_sum_c(cplx v, cplx* red) {        // block_sum over the compute threads
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_sum(v);
-  csync<NC>();
-  if (lane == 0) red[warp] = v;
-  csync<NC>();
-  cplx t = make_double2(0.0, 0.0);
-  for (int i = 0; i < NC / 32; ++i) t = cadd(t, red[i]);
-  return t;
-}
-template <int NC> __device__ __forceinline__ void larfg_block_c(const cplx* xs, cplx* vs, int ln, cplx* red, cplx& tau, double& beta) {
-  const int tid = threadIdx.x;
-  cplx nrm = make_double2(0.0, 0.0);
-  for (int i = 1 + tid; i < ln; i += NC) { const cplx a = xs[i]; nrm.x += a.x * a.x + a.y * a.y; }
-  nrm = block_sum_c<NC>(nrm, red);
-  const cplx alpha = xs[0];
-  cplx scale;
-  if (nrm.x == 0.0 && alpha.y == 0.0) {
-    beta = alpha.x;
-    tau = make_double2(0.0, 0.0);
-    scale = make_double2(0.0, 0.0);
-  } else {
-    beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm.x), alpha.x);
-    tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-    const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
-    scale = make_double2(dr / den, -di / den);
-  }
-  for (int i = tid; i < ln; i += NC) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
-  csync<NC>();
-}
-
 __host__ __device__ constexpr int chase_nc(int tr, int tc) { return (tr * tc + 31) / 32 * 32; }
 // thread-columns per piece of the carried block (helper-warp kernel)
 __host__ __device__ constexpr int chase_pcc(int cb) { return DWHMC_CHASE_PCC; }
