@@ -83,14 +83,17 @@ def _put(AB, B, r0, c0):
                 AB[d, c0 + jj] = B[ii, jj]
 
 
-def chase_band(A, b):
+def chase_band(A, b, dense_tail=False):
     """Hermitian A of half-bandwidth b -> (d, e, V, TAU): real tridiagonal (d, e); V[:, s] holds the
-    reflectors of sweep s at their row positions, TAU[s, k] their tau."""
+    reflectors of sweep s at their row positions, TAU[s, k] their tau.  dense_tail: the last b sweeps
+    (one step each) as a dense tridiagonalisation of the trailing (b+1) x (b+1) block, the way
+    chase_tail_kernel does them in shared memory."""
     n = A.shape[0]
     AB = to_band(A, b)
     V = np.zeros((n, n), complex)
     TAU = np.zeros((n, (n + b - 1) // b + 1), complex)
-    for s in range(n - 1):
+    nsweep = n - 1 - b if dense_tail and n - 1 - b >= 1 else n - 1
+    for s in range(nsweep):
         k, r0 = 0, s + 1
         Bc = us = vp = None
         taup = 0.0
@@ -124,6 +127,24 @@ def chase_band(A, b):
             Bc = _get(AB, r1, min(b, n - r1), r0, ln)
             us, vp, taup = Bc @ v, v, tau
             r0, k = r1, k + 1
+    if nsweep < n - 1:
+        s0, m0 = n - 1 - b, b + 1
+        F = _get(AB, s0, m0, s0, m0)       # trailing block: full storage from the lower band
+        F = np.tril(F) + np.tril(F, -1).conj().T
+        for j in range(b):
+            v, tau, beta = larfg(F[j + 1:, j].copy())
+            V[s0 + j + 1:, s0 + j] = v
+            TAU[s0 + j, 0] = tau
+            A22 = F[j + 1:, j + 1:]
+            y = tau * (A22 @ v)
+            w = y - 0.5 * tau * np.vdot(y, v) * v
+            F[j + 1:, j + 1:] = A22 - np.outer(v, w.conj()) - np.outer(w, v.conj())
+            F[j + 1:, j] = 0
+            F[j + 1, j] = beta
+        for c in range(m0):
+            AB[0, s0 + c] = F[c, c].real
+            if c + 1 < m0:
+                AB[1, s0 + c] = F[c + 1, c].real
     return AB[0, :].real.copy(), AB[1, :n - 1].real.copy(), V, TAU
 
 

@@ -50,3 +50,9 @@ def test_band_route_prototype_matches_lapack():
         assert np.max(np.abs(U.conj().T @ U - np.eye(n))) <= 1e-12
         Uw = apb.backtransform_wavefronts(Z, V, TAU, b, g)          # the launch order of the fused kernel
         assert np.max(np.abs(Uw - U)) <= 1e-13
+        # the last b sweeps as a dense tridiagonalisation of the trailing block (chase_tail_kernel): same tridiagonal
+        # matrix, reflectors and tau as the bulge chase produces for those single-step sweeps
+        d2, e2, V2, TAU2 = apb.chase_band(Hp, b, dense_tail=True)
+        scale = np.max(np.abs(w))
+        assert np.max(np.abs(d2 - d)) <= 1e-12 * scale and np.max(np.abs(e2 - e)) <= 1e-12 * scale
+        assert np.max(np.abs(V2 - V)) <= 1e-11 and np.max(np.abs(TAU2 - TAU)) <= 1e-11
