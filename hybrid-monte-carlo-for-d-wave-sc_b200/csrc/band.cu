@@ -1427,263 +1427,6 @@ __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restric
   e[(size_t)b * n + j] = (j + 1 < n) ? col[1].x : 0.0;
 }
 
-// ---- block reflectors of the back-transformation ---------------------------------------------------
-// block (s0, k): columns s0 .. s0+g-1 of V, rows rlo = s0+1+kb .. ; column c is non-zero on rows
-// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block.
-constexpr int TG = 64;               // max reflectors per block
-__global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restrict__ Vall, const cplx* __restrict__ tau2,
-                                                           cplx* __restrict__ Tall, cplx* __restrict__ VTall,
-                                                           const int* __restrict__ blk_s0, const int* __restrict__ blk_k,
-                                                           int n, int b, int g, int KT, int nblk, Mask mask) {
-  const int blk = blockIdx.x, ch = blockIdx.y;
-  if (!mask.on(ch)) return;
-  __shared__ cplx Vs[32 * (TG + 1)];     // row chunk [32 rows][g columns], column index fastest
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* G = reinterpret_cast<cplx*>(smem_raw);          // [g][g] column-major
-  cplx* T = G + g * g;                                   // [g][g+1] row-major rows
-  const int s0 = blk_s0[blk], k = blk_k[blk];
-  const int gg = min(g, n - 1 - s0);                     // sweeps s0 .. s0+gg-1 exist
-  const int rlo = s0 + 1 + k * b;
-  const int rows = min(n - rlo, b + gg - 1);
-  const cplx* V = Vall + (size_t)ch * n * n;
-  const int tid = threadIdx.x;
-  const cplx zero = make_double2(0.0, 0.0);
-  // Gram matrix, lower part computed (c1 >= c2), accumulated over row chunks
-  constexpr int PAIRS = (TG * TG + 255) / 256;
-  cplx acc[PAIRS];
-#pragma unroll
-  for (int q = 0; q < PAIRS; ++q) acc[q] = zero;
-  for (int rc = 0; rc < rows; rc += 32) {
-    __syncthreads();
-    for (int idx = tid; idx < 32 * gg; idx += 256) {
-      const int r = idx & 31, c = idx >> 5;
-      const int rr = rc + r;
-      const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
-      Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < PAIRS; ++q) {
-      const int pidx = tid + 256 * q;
-      const int c1 = pidx % g, c2 = pidx / g;
-      if (c2 < gg && c1 < gg) {
-        cplx a = acc[q];
-        for (int r = 0; r < 32; ++r) cfmac(a, Vs[r * (TG + 1) + c1], Vs[r * (TG + 1) + c2]);
-        acc[q] = a;
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < PAIRS; ++q) {
-    const int pidx = tid + 256 * q;
-    const int c1 = pidx % g, c2 = pidx / g;
-    if (c2 < g && c1 < g) G[c2 * g + c1] = (c2 < gg && c1 < gg) ? acc[q] : zero;   // G[c1, c2] = v_c1^H v_c2
-  }
-  for (int idx = tid; idx < g * (g + 1); idx += 256) T[idx] = zero;
-  __syncthreads();
-  // T[i,i] = tau_i ; T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i] ; thread r owns row r
-  if (tid < g) {
-    const int r = tid;
-    cplx* Tr = T + r * (g + 1);
-    for (int i = 0; i < gg; ++i) {
-      const cplx t = tau2[((size_t)ch * n + s0 + i) * KT + k];
-      if (r < i) {
-        cplx s = zero;
-        for (int l = r; l < i; ++l) cfma(s, Tr[l], G[i * g + l]);
-        Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
-      } else if (r == i) {
-        Tr[i] = t;
-      }
-    }
-  }
-  __syncthreads();
-  cplx* out = Tall + ((size_t)ch * nblk + blk) * TG * TG;     // column-major, ld = TG
-  for (int idx = tid; idx < g * g; idx += 256) {
-    const int r = idx % g, c = idx / g;
-    out[c * TG + r] = T[r * (g + 1) + c];
-  }
-  // VT = Vb T for the fused back-transformation kernel: [32 columns][128 rows] per block, zero padded
-  if (VTall != nullptr) {
-    cplx* vt = VTall + ((size_t)ch * nblk + blk) * (32 * 128);
-    for (int rc = 0; rc < 128; rc += 32) {
-      __syncthreads();
-      for (int idx = tid; idx < 32 * gg; idx += 256) {
-        const int r = idx & 31, c = idx >> 5;
-        const int rr = rc + r;
-        const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
-        Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
-      }
-      __syncthreads();
-      for (int idx = tid; idx < 32 * 32; idx += 256) {
-        const int r = idx & 31, m = idx >> 5;
-        cplx a = zero;
-        if (m < gg && rc + r < rows)
-          for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
-        vt[m * 128 + rc + r] = a;
-      }
-    }
-  }
-}
-
-// ---- fused staircase block reflector: Z[R, :] -= (Vb T) (Vb^H Z[R, :]) ---------------------------------
-// One CTA = (column part, block of the wavefront, chain).  Vb (<= 128 rows x <= 32 reflectors, zero outside the
-// staircase) and VT = Vb T (from band_tfactor_kernel) stay in shared memory; the CTA walks its column tiles of 16 with cp.async double
-// buffering and runs two products per tile on the FP64 tensor cores (DMMA m8n8k4, four real DMMAs per complex
-// product):   W1 = Vb^H Zt (32 x 16, K = 128),   Zt - VT W1 (128 x 16, K = 32) written straight to global memory.
-// Blocks of one wavefront t = (Gmax - G) + k touch disjoint rows and only depend on smaller t.
-constexpr int AR = 128, AG = 32, ANC = 16;
-// leading dimensions chosen per access pattern (16-byte elements, eight lanes per wavefront): operands read as
-// (row = lane / 4, k = lane % 4) need ld = 4 mod 8, operands read as (k = lane % 4, row = lane / 4) need ld = 2 mod 4
-constexpr int ALDV = 132, ALDVT = 130, ALDZ = 132, ALDW = 36;
-constexpr int ATH = 512;             // 16 warps: four per scheduler keep the tensor pipe fed across barriers
-constexpr size_t APPLY_SMEM = sizeof(cplx) * ((size_t)AG * ALDV + AG * ALDVT + 2 * ANC * ALDZ + 2 * ANC * ALDW);
-
-__device__ __forceinline__ void cp16(void* smem, const void* gmem, bool pred) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
-}
-
-__global__ void __launch_bounds__(ATH, 1) band_apply_kernel(cplx* __restrict__ Zall, const cplx* __restrict__ Vall,
-                                                            const cplx* __restrict__ VTall, const int* __restrict__ blk_s0,
-                                                            const int* __restrict__ blk_k, const int* __restrict__ wave_blk,
-                                                            const int* __restrict__ halfflag, int n, int b, int g, int nblk,
-                                                            int c_lo, int use_half, Mask mask) {
-  using dwg::dmma884;
-  const int chain = blockIdx.z;
-  if (!mask.on(chain)) return;
-  const int blk = wave_blk[blockIdx.y];
-  const int s0 = blk_s0[blk], k = blk_k[blk];
-  const int gg = min(g, n - 1 - s0);
-  const int rlo = s0 + 1 + k * b;
-  const int rows = min(n - rlo, b + gg - 1);
-  if (rows <= 0 || gg <= 0) return;
-  const int cstart = (use_half && halfflag[chain] != 0) ? c_lo : 0;
-  const int ntile = (n - cstart + ANC - 1) / ANC;
-  const int per = (ntile + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(ntile, t0 + per);
-  if (t0 >= t1) return;
-  extern __shared__ __align__(16) unsigned char smem_apply[];
-  cplx* Vs = reinterpret_cast<cplx*>(smem_apply);   // [AG][ALDV]  Vs[m * ALDV + r] = Vb[r][m]
-  cplx* VTs = Vs + AG * ALDV;                         // [AG][ALDVT] (Vb T)[r][m]
-  cplx* Zs = VTs + AG * ALDVT;                         // [2][ANC][ALDZ]
-  cplx* W1s = Zs + 2 * ANC * ALDZ;                    // [2 K halves][ANC][ALDW]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fr = lane >> 2, fk = lane & 3;
-  const cplx zero = make_double2(0.0, 0.0);
-  const cplx* V = Vall + (size_t)chain * n * n;
-  cplx* Z = Zall + (size_t)chain * n * n;
-  const cplx* VT = VTall + ((size_t)chain * nblk + blk) * (AG * AR);
-  for (int idx = tid; idx < AG * AR; idx += ATH) {
-    const int r = idx % AR, m = idx / AR;
-    const bool ok = m < gg && r < rows && r - m >= 0 && r - m < b;
-    Vs[m * ALDV + r] = ok ? V[(size_t)(s0 + m) * n + rlo + r] : zero;
-    VTs[m * ALDVT + r] = VT[idx];
-  }
-  __syncthreads();
-  auto load_tile = [&](int t, int buf) {
-    cplx* dst = Zs + buf * ANC * ALDZ;
-    const int col0 = cstart + t * ANC;
-#pragma unroll
-    for (int it = 0; it < (ANC * AR) / ATH; ++it) {
-      const int idx = tid + it * ATH;
-      const int r = idx % AR, c = idx / AR;
-      const bool ok = r < rows && col0 + c < n;
-      cp16(dst + c * ALDZ + r, ok ? Z + (size_t)(col0 + c) * n + rlo + r : Z, ok);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-  load_tile(t0, 0);
-  const int kmax = (rows + 3) & ~3;                   // K range of the first product (rows beyond are zero)
-  for (int t = t0; t < t1; ++t) {
-    const int buf = (t - t0) & 1;
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();                                  // tile t landed; everyone is done with the other buffer
-    if (t + 1 < t1) load_tile(t + 1, buf ^ 1);
-    cplx* Zt = Zs + buf * ANC * ALDZ;
-    // ---- W1 = Vb^H Zt : warp -> (tile mt = w % 4, nt = (w / 4) % 2, K half w / 8); two accumulator sets over
-    //      alternating k-steps keep four independent DMMA chains in flight
-    {
-      const int mt = warp & 3, nt = (warp >> 2) & 1, kh = warp >> 3;
-      // reflectors 8 mt .. 8 mt + 7 are non-zero on rows 8 mt .. 8 mt + 6 + b only (staircase)
-      const int klo = mt * 8, khi = min(kmax, (mt * 8 + 7 + b + 3) & ~3);
-      const int kmid = min(khi, klo + (((khi - klo) / 2 + 7) & ~7));
-      const int kb = kh ? kmid : klo, ke = kh ? khi : kmid;
-      double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0, dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
-      const cplx* ap = Vs + (mt * 8 + fr) * ALDV + fk;
-      const cplx* bp = Zt + (nt * 8 + fr) * ALDZ + fk;
-      for (int k0 = kb; k0 < ke; k0 += 8) {
-        const cplx a = ap[k0], bb = bp[k0];
-        const bool two = k0 + 4 < ke;
-        const cplx a2 = two ? ap[k0 + 4] : zero, b2 = two ? bp[k0 + 4] : zero;
-        dmma884(cr0, cr1, a.x, bb.x);
-        dmma884(ci0, ci1, a.x, bb.y);
-        dmma884(dr0, dr1, a2.x, b2.x);
-        dmma884(di0, di1, a2.x, b2.y);
-        dmma884(cr0, cr1, a.y, bb.y);
-        dmma884(ci0, ci1, -a.y, bb.x);
-        dmma884(dr0, dr1, a2.y, b2.y);
-        dmma884(di0, di1, -a2.y, b2.x);
-      }
-      cplx* w = W1s + kh * ANC * ALDW;
-      w[(nt * 8 + 2 * fk) * ALDW + mt * 8 + fr] = make_double2(cr0 + dr0, ci0 + di0);
-      w[(nt * 8 + 2 * fk + 1) * ALDW + mt * 8 + fr] = make_double2(cr1 + dr1, ci1 + di1);
-    }
-    __syncthreads();
-    // ---- Zt - VT W1 -> global : warp -> row tile, both column tiles
-    if (warp * 8 < rows) {
-      double cr[2][2], ci[2][2];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const cplx c = Zt[(nt * 8 + 2 * fk + e) * ALDZ + warp * 8 + fr];
-          cr[nt][e] = c.x; ci[nt][e] = c.y;
-        }
-#pragma unroll
-      for (int k0 = 0; k0 < AG; k0 += 4) {
-        const cplx a = VTs[(k0 + fk) * ALDVT + warp * 8 + fr];
-        cplx bb[2];
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const cplx p0 = W1s[(nt * 8 + fr) * ALDW + k0 + fk], p1 = W1s[ANC * ALDW + (nt * 8 + fr) * ALDW + k0 + fk];
-          bb[nt] = make_double2(p0.x + p1.x, p0.y + p1.y);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          dmma884(cr[nt][0], cr[nt][1], -a.x, bb[nt].x);
-          dmma884(ci[nt][0], ci[nt][1], -a.x, bb[nt].y);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          dmma884(cr[nt][0], cr[nt][1], a.y, bb[nt].y);
-          dmma884(ci[nt][0], ci[nt][1], -a.y, bb[nt].x);
-        }
-      }
-      const int col0 = cstart + t * ANC;
-      const int r = warp * 8 + fr;
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = col0 + nt * 8 + 2 * fk + e;
-          if (r < rows && c < n) Z[(size_t)c * n + rlo + r] = make_double2(cr[nt][e], ci[nt][e]);
-        }
-    }
-  }
-}
-
-// rows back to the reference's order: U[r, c] = Zb[pos[r], c]
-__global__ void __launch_bounds__(256) band_unpermute_kernel(const cplx* __restrict__ Zall, cplx* __restrict__ Uall,
-                                                             const int* __restrict__ pos, const int* __restrict__ halfflag,
-                                                             int c_lo, int n, Mask mask) {
-  const int b = blockIdx.y, c = blockIdx.x;
-  if (!mask.on(b)) return;
-  if (c < c_lo && halfflag[b] != 0) return;
-  const cplx* src = Zall + (size_t)b * n * n + (size_t)c * n;
-  cplx* dst = Uall + (size_t)b * n * n + (size_t)c * n;
-  for (int r = threadIdx.x; r < n; r += blockDim.x) dst[r] = src[pos[r]];
-}
 
 }  // namespace
 
@@ -1743,13 +1486,12 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
   const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
   // the chase kernel keeps 20 block elements per thread in registers: b^2 <= 20 * 512
   if (!want || 3 * bw > n || bw > 32 * RQ || (size_t)bw * bw > (size_t)EU * CT || smem > 225 * 1024) return DWHMC_OK;   // dense route
+  // reflectors per block of the back-transformation (band_apply.cu): 32, block height b + 31 <= 136 rows
+  if (bw + DW_APPLY_G - 1 > DW_APPLY_ROWS) return DWHMC_OK;                                // dense route
+  const int g = DW_APPLY_G;
   h->band_b = bw;
   h->band_LD = 2 * bw;
   h->band_KT = (n + bw - 1) / bw + 1;
-  // reflectors per block of the back-transformation: block height b + g - 1 a multiple of 64
-  int g = 64 * ((bw + 16 + 63) / 64) - bw + 1;
-  g = std::max(8, std::min(g, TG));
-  if (bw + 8 <= AR) g = std::min(AG, AR - bw + 1);      // fused block-reflector kernel: <= 32 reflectors, <= 128 rows
   h->band_g = g;
   // block list, application order: sweep groups last to first, steps ascending
   std::vector<int> bs0, bk;
@@ -1944,89 +1686,3 @@ int dw_band_chase(Handle* h, Mask mask) {
   return DWHMC_OK;
 }
 
-// Zb (n x n complex, band row order, in h->A) <- Q2 Zb, then rows back to site order into U
-// T factors of all staircase blocks (needs only the chase output, so it can run beside the D&C stage)
-int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream) {
-  const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
-  const int nblk = (int)h->band_blk_s0.size();
-  const size_t smem = sizeof(cplx) * ((size_t)g * g + (size_t)g * (g + 1));
-  static bool attr_set[64] = {false};
-  if (!attr_set[h->device & 63]) {
-    DW_CUDA(h, cudaFuncSetAttribute(band_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set[h->device & 63] = true;
-  }
-  dim3 grid(nblk, B);
-  band_tfactor_kernel<<<grid, 256, smem, stream>>>(h->V, h->band_tau, h->band_T, h->band_VT, h->band_blk_s0_dev,
-                                                   h->band_blk_k_dev, n, bw, g, h->band_KT, nblk, mask);
-  DW_LAUNCH_CHECK(h);
-  return DWHMC_OK;
-}
-
-int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
-  const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
-  const int nblk = (int)h->band_blk_s0.size();
-  const bool half = ph && h->ph_mode;
-  ZgemmArgs a;
-  a.nseg = 1; a.A[1] = nullptr; a.Bm[1] = nullptr; a.lower = 0; a.batch = B; a.mask = mask;
-  if (half) { a.skip_flag = h->halfflag; a.skip_cols = h->N; }
-  cplx* Z = h->A;
-  static const bool no_fused = getenv("DWHMC_BAND_NOFUSE") != nullptr;
-  const bool fused = !no_fused && g <= AG && bw + g - 1 <= AR;
-  if (fused) {
-    static bool fattr[64] = {false};
-    if (!fattr[h->device & 63]) {
-      DW_CUDA(h, cudaFuncSetAttribute(band_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APPLY_SMEM));
-      fattr[h->device & 63] = true;
-    }
-    const int c_lo = half ? (h->N / ANC) * ANC : 0;        // 16-column tiles: no straddling columns to carry
-    const int nwave = (int)h->band_wave_start.size() - 1;
-    for (int t = 0; t < nwave; ++t) {
-      const int w0 = h->band_wave_start[t], nsub = h->band_wave_start[t + 1] - w0;
-      if (nsub <= 0) continue;
-      // column parts per block: enough CTAs for ~4 waves, as few as possible (each CTA rebuilds V T)
-      const int nparts = std::max(2, std::min(8, (4 * h->nsm + nsub * B - 1) / (nsub * B)));
-      dim3 grid(nparts, nsub, B);
-      band_apply_kernel<<<grid, ATH, APPLY_SMEM, h->stream>>>(Z, h->V, h->band_VT, h->band_blk_s0_dev, h->band_blk_k_dev,
-                                                               h->band_wave_dev + w0, h->halfflag, n, bw, g, nblk, c_lo,
-                                                               half ? 1 : 0, mask);
-      DW_LAUNCH_CHECK(h);
-    }
-  }
-  for (int blk = 0; blk < nblk && !fused; ++blk) {
-    const int s0 = h->band_blk_s0[blk], k = h->band_blk_k[blk];
-    const int gg = std::min(g, n - 1 - s0);
-    const int rlo = s0 + 1 + k * bw;
-    const int rows = std::min(n - rlo, bw + gg - 1);
-    if (rows <= 0 || gg <= 0) continue;
-    const cplx* Vb = h->V + (size_t)s0 * n + rlo;
-    cplx* Zb = Z + rlo;
-    // W1 (gg x n) = Vb^H Zb
-    a.M = gg; a.N = n; a.K = rows;
-    a.A[0] = Vb; a.lda = n; a.sA = (long long)n * n; a.opA = 1; a.stairA = bw;
-    a.Bm[0] = Zb; a.ldb = n; a.sB = (long long)n * n; a.opB = 0;
-    a.C = h->Wbt; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
-    a.alpha = 1.0; a.beta = 0.0;
-    DW_TRY(dw_zgemm(h, a));
-    // W2 = T W1
-    a.M = gg; a.N = n; a.K = gg; a.stairA = 0;
-    a.A[0] = h->band_T + (size_t)blk * TG * TG; a.lda = TG; a.sA = (long long)nblk * TG * TG; a.opA = 0;
-    a.Bm[0] = h->Wbt; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
-    a.C = h->Wbt2; a.ldc = DW_NBT; a.sC = (long long)DW_NBT * n;
-    a.alpha = 1.0; a.beta = 0.0;
-    DW_TRY(dw_zgemm(h, a));
-    // Zb -= Vb W2
-    a.M = rows; a.N = n; a.K = gg; a.stairA = bw;
-    a.A[0] = Vb; a.lda = n; a.sA = (long long)n * n; a.opA = 0;
-    a.Bm[0] = h->Wbt2; a.ldb = DW_NBT; a.sB = (long long)DW_NBT * n; a.opB = 0;
-    a.C = Zb; a.ldc = n; a.sC = (long long)n * n;
-    a.alpha = -1.0; a.beta = 1.0;
-    DW_TRY(dw_zgemm(h, a));
-  }
-  {
-    dim3 grid(n, B);
-    const int c_lo = half ? (fused ? (h->N / ANC) * ANC : (h->N / 128) * 128) : 0;
-    band_unpermute_kernel<<<grid, 256, 0, h->stream>>>(Z, U, h->band_pos, h->halfflag, c_lo, n, mask);
-    DW_LAUNCH_CHECK(h);
-  }
-  return DWHMC_OK;
-}

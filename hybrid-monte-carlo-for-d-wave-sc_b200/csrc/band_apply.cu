@@ -1,0 +1,397 @@
+// band_apply.cu -- back-transformation of the band route: U = Q2 Z (/root/reference src/Hamiltonian.jl:106-111,
+// the eigenvectors eigen! returns).  Q2 is the product of the Householder reflectors of the bulge chase (band.cu);
+// the reflectors of g consecutive sweeps at the same step form one staircase block reflector I - Vb T Vb^H.
+//   band_tfactor_kernel   T and Vb T per block (runs beside the D&C stage)
+//   band_apply2_kernel    the block reflectors on the FP64 tensor cores, Z strips held in registers
+//   band_unpermute_kernel rows back to the reference's site order
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "dwhmc.h"
+#include "gemm_dmma.cuh"
+#include "internal.h"
+
+namespace {
+
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {       // acc += a b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(cplx& acc, cplx a, cplx b) {      // acc += conj(a) b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+
+// ---- block reflectors of the back-transformation ---------------------------------------------------
+// block (s0, k): columns s0 .. s0+g-1 of V, rows rlo = s0+1+kb .. ; column c is non-zero on rows
+// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block.
+constexpr int A2_MT = 4;                 // tiles of 8 reflectors: up to 32 reflectors per block
+constexpr int A2_G = 8 * A2_MT;
+constexpr int A2_NRT = 17;               // tiles of 8 rows: blocks of up to 136 rows (b + g - 1)
+constexpr int A2_ROWS = 8 * A2_NRT;
+constexpr int A2_WARPS = 8;              // 255 registers per thread: the whole row range of a strip lives in registers
+constexpr int A2_TH = 32 * A2_WARPS;
+// odd leading dimension 8 NRT + 1: both operand read patterns are conflict-free
+constexpr size_t apply2_smem(int nrt) { return sizeof(cplx) * 2 * (size_t)A2_G * (8 * nrt + 1); }
+
+static_assert(A2_G == DW_APPLY_G && A2_ROWS == DW_APPLY_ROWS, "internal.h");
+
+// ---- T factors ------------------------------------------------------------------------------------------
+// block (s0, k): columns s0 .. s0+g-1 of V, rows rlo = s0+1+kb .. ; column c is non-zero on rows
+// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block; the output is
+// -Vb T, [A2_G reflectors][A2_ROWS rows] per block, zero padded (what band_apply2_kernel keeps in shared memory).
+__global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restrict__ Vall, const cplx* __restrict__ tau2,
+                                                           cplx* __restrict__ NVTall, const int* __restrict__ blk_s0,
+                                                           const int* __restrict__ blk_k, int n, int b, int g, int KT,
+                                                           int nblk, Mask mask) {
+  constexpr int TG = A2_G;
+  const int blk = blockIdx.x, ch = blockIdx.y;
+  if (!mask.on(ch)) return;
+  extern __shared__ __align__(16) unsigned char smem_tf[];
+  cplx* Vs = reinterpret_cast<cplx*>(smem_tf);   // [32][TG + 1] row chunk [32 rows][g columns], column index fastest
+  cplx* G = Vs + 32 * (TG + 1);                   // [g][g] column-major
+  cplx* T = G + TG * TG;                          // [g][g+1] row-major rows
+  const int s0 = blk_s0[blk], k = blk_k[blk];
+  const int gg = min(g, n - 1 - s0);                     // sweeps s0 .. s0+gg-1 exist
+  const int rlo = s0 + 1 + k * b;
+  const int rows = min(n - rlo, b + gg - 1);
+  const cplx* V = Vall + (size_t)ch * n * n;
+  const int tid = threadIdx.x;
+  const cplx zero = make_double2(0.0, 0.0);
+  auto load_chunk = [&](int rc) {
+    for (int idx = tid; idx < 32 * gg; idx += 256) {
+      const int r = idx & 31, c = idx >> 5;
+      const int rr = rc + r;
+      const bool ok = rr < rows && rr - c >= 0 && rr - c < b;
+      Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
+    }
+  };
+  // Gram matrix, accumulated over row chunks
+  constexpr int PAIRS = (TG * TG + 255) / 256;
+  cplx acc[PAIRS];
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) acc[q] = zero;
+  for (int rc = 0; rc < rows; rc += 32) {
+    __syncthreads();
+    load_chunk(rc);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+      const int pidx = tid + 256 * q;
+      const int c1 = pidx % g, c2 = pidx / g;
+      if (c2 < gg && c1 < gg) {
+        cplx a = acc[q];
+        for (int r = 0; r < 32; ++r) cfmac(a, Vs[r * (TG + 1) + c1], Vs[r * (TG + 1) + c2]);
+        acc[q] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PAIRS; ++q) {
+    const int pidx = tid + 256 * q;
+    const int c1 = pidx % g, c2 = pidx / g;
+    if (c2 < g && c1 < g) G[c2 * g + c1] = (c2 < gg && c1 < gg) ? acc[q] : zero;   // G[c1, c2] = v_c1^H v_c2
+  }
+  for (int idx = tid; idx < g * (g + 1); idx += 256) T[idx] = zero;
+  __syncthreads();
+  // T[i,i] = tau_i ; T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i] ; thread r owns row r
+  if (tid < g) {
+    const int r = tid;
+    cplx* Tr = T + r * (g + 1);
+    for (int i = 0; i < gg; ++i) {
+      const cplx t = tau2[((size_t)ch * n + s0 + i) * KT + k];
+      if (r < i) {
+        cplx s = zero;
+        for (int l = r; l < i; ++l) cfma(s, Tr[l], G[i * g + l]);
+        Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
+      } else if (r == i) {
+        Tr[i] = t;
+      }
+    }
+  }
+  // -Vb T
+  cplx* nvt = NVTall + ((size_t)ch * nblk + blk) * (A2_G * A2_ROWS);
+  for (int rc = 0; rc < A2_ROWS; rc += 32) {
+    __syncthreads();
+    load_chunk(rc);
+    __syncthreads();
+    for (int idx = tid; idx < 32 * A2_G; idx += 256) {
+      const int r = idx & 31, m = idx >> 5;
+      if (rc + r >= A2_ROWS) continue;
+      cplx a = zero;
+      if (m < gg && rc + r < rows)
+        for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
+      nvt[m * A2_ROWS + rc + r] = make_double2(-a.x, -a.y);
+    }
+  }
+}
+
+// ---- staircase block reflectors on the FP64 tensor cores: Z[R, :] -= (Vb T) (Vb^H Z[R, :]) -------------------
+// Work item = (block, column part, chain).  conj(Vb) and -Vb T (<= 136 rows x 32 reflectors, zero outside the
+// staircase) sit in shared memory; every warp owns strips of 8 columns of Z and keeps the whole row range of
+// a strip in registers, transposed: the DMMA m8n8k4 tile Z^T[8 columns][8 rows] is at once
+//   * the A operand of the first product  W^T (8 columns x 32 reflectors) = Z^T conj(Vb)   (k runs over rows), and
+//   * the accumulator of the second one   Z^T -= W^T (Vb T)^T                               (k runs over reflectors),
+// because the order of the k index inside a dot product is free: lane (column, c) holds rows 2c and 2c+1 of a
+// row tile as accumulator elements and uses exactly these two rows as its k entries of two k-steps (the shared-
+// memory operand is read with the same permutation); likewise W^T comes out of the first product in accumulator
+// layout and goes into the second as the A operand unchanged.  So Z is read from global memory once, updated in
+// registers and written once, there is no shared-memory staging of Z, no transposition and no block barrier
+// inside an item; four real DMMAs per complex product, k-steps outside the staircase are skipped.
+// Items are handed out by a ticket counter in wavefront order (t = (Gmax - G) + k: blocks of one wavefront touch
+// disjoint rows and only depend on smaller t); an item waits until the items of the previous wavefront of its
+// (chain, column part) have been published, so one launch runs the whole back-transformation.
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double dneg(double x) {      // sign flip on the integer pipe
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+__device__ __forceinline__ cplx ldcg(const cplx* p) {   // L2 only: Z is shared between CTAs across wavefronts
+  cplx v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct Apply2Args {
+  cplx* Z; const cplx* V; const cplx* NVT;
+  const int* blk_s0; const int* blk_k;
+  const int4* items;             // per chain, wavefront order: (block, column part, wavefront, blocks of the previous wavefront)
+  int item0, item1;              // range of items of this launch (all of them, or one wavefront)
+  int* ticket;                   // [1]
+  int* done;                     // [B][nparts][nwave] published items
+  int* status;                   // [>= 3]: [2] set if a wait timed out
+  const int* halfflag;
+  int n, b, g, nblk, B, nparts, nwave, c_lo, use_half;
+  Mask mask;
+};
+
+// NRT: row tiles of a block, 8 NRT >= b + 31.  Reflector tile mt (reflectors 8 mt .. 8 mt + 7) is non-zero on rows
+// 8 mt .. 8 mt + 6 + b, columns 8 mt .. of -Vb T on rows 0 .. 8 mt + 6 + b: row tiles rt with rt - mt > SK = NRT - 4
+// (>= (b + 6) / 8) or rt < mt are skipped at compile time; partial blocks at the matrix end are zero padded.
+template <int NRT>
+__global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
+  constexpr int ROWS = 8 * NRT, LDV = ROWS + 1, SK = NRT - 4;
+  extern __shared__ __align__(16) unsigned char smem_apply[];
+  cplx* CV = reinterpret_cast<cplx*>(smem_apply);    // [A2_G][LDV]  conj(Vb)[r][m] at m * LDV + r
+  cplx* NVT = CV + A2_G * LDV;                        // [A2_G][LDV]  -(Vb T)[r][m]
+  __shared__ int s_q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int n = a.n, b = a.b;
+  const cplx zero = make_double2(0.0, 0.0);
+  const int total = (a.item1 - a.item0) * a.B;
+  for (;;) {
+    __syncthreads();                                  // everyone is done with shared memory and s_q
+    if (tid == 0) s_q = atomicAdd(a.ticket, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= total) return;
+    const int chain = q % a.B;
+    if (!a.mask.on(chain)) continue;
+    const int4 it = a.items[a.item0 + q / a.B];
+    const int blk = it.x, part = it.y, wave = it.z;
+    const int s0 = a.blk_s0[blk], k = a.blk_k[blk];
+    const int gg = min(a.g, n - 1 - s0);
+    const int rlo = s0 + 1 + k * b;
+    const int rows = min(n - rlo, b + gg - 1);
+    int* done = a.done + ((size_t)chain * a.nparts + part) * a.nwave;
+    const int cstart = (a.use_half && a.halfflag[chain] != 0) ? a.c_lo : 0;
+    const int nstrip = (n - cstart + 7) >> 3;
+    const int per = (nstrip + a.nparts - 1) / a.nparts;
+    const int st0 = part * per, st1 = min(nstrip, st0 + per);
+    if (rows > 0 && gg > 0 && st0 < st1) {
+      // the blocks of the previous wavefront of this (chain, column part) have to be in global memory
+      if (tid == 0 && wave > 0 && it.w > 0) {
+        int spins = 0;
+        while (ld_acquire(done + wave - 1) < it.w) {
+          __nanosleep(64);
+          if (++spins > (1 << 22)) { atomicExch(a.status + 2, 1); break; }
+        }
+      }
+      const cplx* V = a.V + (size_t)chain * n * n;
+      const cplx* nvt = a.NVT + ((size_t)chain * a.nblk + blk) * (A2_G * A2_ROWS);
+      for (int idx = tid; idx < A2_G * ROWS; idx += A2_TH) {
+        const int r = idx % ROWS, m = idx / ROWS;
+        const bool ok = m < gg && r < rows && r - m >= 0 && r - m < b;
+        const cplx v = ok ? V[(size_t)(s0 + m) * n + rlo + r] : zero;
+        CV[m * LDV + r] = make_double2(v.x, -v.y);
+        NVT[m * LDV + r] = nvt[m * A2_ROWS + r];
+      }
+      __syncthreads();
+      for (int strip = st0 + warp; strip < st1; strip += A2_WARPS) {
+        const int col = cstart + strip * 8 + fr;
+        const bool colok = col < n;
+        cplx* zc = a.Z + ((size_t)chain * n + (colok ? col : 0)) * n + rlo + 2 * fk;
+        double zr[NRT][2], zi[NRT][2];
+#pragma unroll
+        for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool ok = colok && 8 * rt + 2 * fk + e < rows;
+            const cplx v = ok ? ldcg(zc + 8 * rt + e) : zero;
+            zr[rt][e] = v.x; zi[rt][e] = v.y;
+          }
+        }
+        // ---- W^T = Z^T conj(Vb): accumulator (column fr, reflectors 8 mt + 2 fk + {0, 1})
+        double wr[A2_MT][2], wi[A2_MT][2];
+#pragma unroll
+        for (int mt = 0; mt < A2_MT; ++mt) { wr[mt][0] = wr[mt][1] = wi[mt][0] = wi[mt][1] = 0.0; }
+#pragma unroll
+        for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double ar = zr[rt][e], ai = zi[rt][e], nai = dneg(ai);
+#pragma unroll
+            for (int mt = 0; mt < A2_MT; ++mt) {
+              if (rt < mt || rt - mt > SK) continue;
+              const cplx cv = CV[(8 * mt + fr) * LDV + 8 * rt + 2 * fk + e];
+              dmma(wr[mt][0], wr[mt][1], ar, cv.x);
+              dmma(wi[mt][0], wi[mt][1], ar, cv.y);
+              dmma(wr[mt][0], wr[mt][1], nai, cv.y);
+              dmma(wi[mt][0], wi[mt][1], ai, cv.x);
+            }
+          }
+        }
+        // ---- Z^T += W^T (-Vb T)^T: columns of -Vb T 8 mt .. 8 mt + 7 are non-zero on rows 0 .. 8 mt + 6 + b
+#pragma unroll
+        for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+          for (int mt = 0; mt < A2_MT; ++mt) {
+            if (rt - mt > SK) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const cplx t = NVT[(8 * mt + 2 * fk + e) * LDV + 8 * rt + fr];
+              dmma(zr[rt][0], zr[rt][1], wr[mt][e], t.x);
+              dmma(zi[rt][0], zi[rt][1], wr[mt][e], t.y);
+              dmma(zr[rt][0], zr[rt][1], dneg(wi[mt][e]), t.y);
+              dmma(zi[rt][0], zi[rt][1], wi[mt][e], t.x);
+            }
+          }
+        }
+#pragma unroll
+        for (int rt = 0; rt < NRT; ++rt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (colok && 8 * rt + 2 * fk + e < rows) zc[8 * rt + e] = make_double2(zr[rt][e], zi[rt][e]);
+        }
+      }
+    }
+    // publish: every thread's stores are ordered before the counter update
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(done + wave, 1);
+  }
+}
+
+// rows back to the reference's order: U[r, c] = Zb[pos[r], c]
+__global__ void __launch_bounds__(256) band_unpermute_kernel(const cplx* __restrict__ Zall, cplx* __restrict__ Uall,
+                                                             const int* __restrict__ pos, const int* __restrict__ halfflag,
+                                                             int c_lo, int n, Mask mask) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  if (!mask.on(b)) return;
+  if (c < c_lo && halfflag[b] != 0) return;
+  const cplx* src = Zall + (size_t)b * n * n + (size_t)c * n;
+  cplx* dst = Uall + (size_t)b * n * n + (size_t)c * n;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) dst[r] = src[pos[r]];
+}
+
+}  // namespace
+
+// -Vb T of all staircase blocks (needs only the chase output, so it can run beside the D&C stage)
+int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream) {
+  const int n = h->n, B = h->B, bw = h->band_b, g = h->band_g;
+  const int nblk = (int)h->band_blk_s0.size();
+  dim3 grid(nblk, B);
+  constexpr size_t smem = sizeof(cplx) * (32 * (A2_G + 1) + A2_G * A2_G + A2_G * (A2_G + 1));
+  static bool attr_set[64] = {false};
+  if (!attr_set[h->device & 63]) {
+    DW_CUDA(h, cudaFuncSetAttribute(band_tfactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[h->device & 63] = true;
+  }
+  band_tfactor_kernel<<<grid, 256, smem, stream>>>(h->V, h->band_tau, h->band_VT, h->band_blk_s0_dev, h->band_blk_k_dev, n, bw,
+                                                g, h->band_KT, nblk, mask);
+  DW_LAUNCH_CHECK(h);
+  return DWHMC_OK;
+}
+
+// item list of the back-transformation (per chain): wavefront order, (block, column part, wavefront, blocks of the
+// previous wavefront); called once from dwhmc_create after dw_band_setup
+void dw_band_apply_items(Handle* h, std::vector<int>& items4) {
+  const int n = h->n;
+  const int nwave = (int)h->band_wave_start.size() - 1;
+  // column parts: strips of 8 columns, about 24 per part (three per warp) on the half spectrum
+  const int nstrip = (n - (h->N / 16) * 16 + 7) / 8;
+  h->band_nparts = std::max(1, std::min(4, (nstrip + 12) / 24));
+  items4.clear();
+  for (int t = 0; t < nwave; ++t) {
+    const int w0 = h->band_wave_start[t], w1 = h->band_wave_start[t + 1];
+    const int prev = t > 0 ? h->band_wave_start[t] - h->band_wave_start[t - 1] : 0;
+    for (int i = w0; i < w1; ++i)
+      for (int p = 0; p < h->band_nparts; ++p) {
+        items4.push_back(h->band_wave_blk[i]); items4.push_back(p); items4.push_back(t); items4.push_back(prev);
+      }
+  }
+  h->band_nitems = (int)items4.size() / 4;
+}
+
+// Zb (n x n complex, band row order, in h->A) <- Q2 Zb, then rows back to site order into U
+int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
+  const int n = h->n, B = h->B;
+  const bool half = ph && h->ph_mode;
+  cplx* Z = h->A;
+  // kernel instance by the number of row tiles of a block, 8 NRT >= b + 31
+  const int nrt = std::max(8, (h->band_b + A2_G - 1 + 7) / 8);
+  void (*kern)(Apply2Args) = nullptr;
+  switch (nrt) {
+    case 8: kern = band_apply2_kernel<8>; break;    case 9: kern = band_apply2_kernel<9>; break;
+    case 10: kern = band_apply2_kernel<10>; break;  case 11: kern = band_apply2_kernel<11>; break;
+    case 12: kern = band_apply2_kernel<12>; break;  case 13: kern = band_apply2_kernel<13>; break;
+    case 14: kern = band_apply2_kernel<14>; break;  case 15: kern = band_apply2_kernel<15>; break;
+    case 16: kern = band_apply2_kernel<16>; break;  case 17: kern = band_apply2_kernel<17>; break;
+    default: h->err = "dw_band_backtransform: half-bandwidth not supported"; return DWHMC_E_BADARG;
+  }
+  const size_t smem = apply2_smem(nrt);
+  if (h->band_apply_attr != nrt) {
+    DW_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->band_apply_attr = nrt;
+  }
+  const int nwave = (int)h->band_wave_start.size() - 1;
+  const int c_lo = half ? (h->N / 16) * 16 : 0;
+  Apply2Args a;
+  a.Z = Z; a.V = h->V; a.NVT = h->band_VT; a.blk_s0 = h->band_blk_s0_dev; a.blk_k = h->band_blk_k_dev;
+  a.items = reinterpret_cast<const int4*>(h->band_items_dev);
+  a.ticket = h->band_sync; a.done = h->band_sync + 1; a.status = h->status; a.halfflag = h->halfflag;
+  a.n = n; a.b = h->band_b; a.g = h->band_g; a.nblk = (int)h->band_blk_s0.size(); a.B = B; a.nparts = h->band_nparts;
+  a.nwave = nwave; a.c_lo = c_lo; a.use_half = half ? 1 : 0; a.mask = mask;
+  const size_t nsync = 1 + (size_t)B * h->band_nparts * nwave;
+  DW_CUDA(h, cudaMemsetAsync(h->band_sync, 0, sizeof(int) * nsync, h->stream));
+  static const bool per_wave = getenv("DWHMC_APPLY_WAVES") != nullptr;     // debugging: one launch per wavefront
+  if (!per_wave) {
+    a.item0 = 0; a.item1 = h->band_nitems;
+    const int ctas = std::min(h->nsm, std::max(1, a.item1 * B));
+    kern<<<ctas, A2_TH, smem, h->stream>>>(a);
+    DW_LAUNCH_CHECK(h);
+  } else {
+    for (int t = 0; t < nwave; ++t) {
+      a.item0 = h->band_wave_start[t] * h->band_nparts; a.item1 = h->band_wave_start[t + 1] * h->band_nparts;
+      if (a.item1 <= a.item0) continue;
+      DW_CUDA(h, cudaMemsetAsync(h->band_sync, 0, sizeof(int), h->stream));
+      kern<<<std::min(h->nsm, (a.item1 - a.item0) * B), A2_TH, smem, h->stream>>>(a);
+      DW_LAUNCH_CHECK(h);
+    }
+  }
+  {
+    dim3 grid(n, B);
+    band_unpermute_kernel<<<grid, 256, 0, h->stream>>>(Z, U, h->band_pos, h->halfflag, c_lo, n, mask);
+    DW_LAUNCH_CHECK(h);
+  }
+  return DWHMC_OK;
+}

@@ -22,6 +22,8 @@
 #define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
 #define DW_LEAF 36        // largest D&C leaf
 #define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
+#define DW_APPLY_G 32      // reflectors per staircase block of the band route's back-transformation
+#define DW_APPLY_ROWS 136  // rows of such a block (half-bandwidth + DW_APPLY_G - 1 at most)
 #define DW_FCHUNK 32      // eigenvector columns per CTA in the bond-correlator kernel
 
 typedef double2 cplx;
@@ -127,12 +129,14 @@ struct Handle {
   int band_b = 0, band_LD = 0, band_KT = 0, band_g = 0;
   std::vector<int> band_pos_host, band_blk_s0, band_blk_k;
   std::vector<int> band_wave_blk, band_wave_start;   // blocks sorted into wavefronts of independent blocks
-  int* band_wave_dev = nullptr;
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
-  cplx* band_T = nullptr;       // device [nblk*64*64*B]: T factors of the back-transformation blocks
-  cplx* band_VT = nullptr;      // device [nblk*32*128*B]: V T per block (fused back-transformation), or null
+  cplx* band_VT = nullptr;      // device [nblk*DW_APPLY_G*DW_APPLY_ROWS*B]: -V T per block of the back-transformation
+  int band_nparts = 1, band_nitems = 0;   // column parts per block; work items per chain (blocks x parts, wavefront order)
+  int band_apply_attr = 0;                // row tiles of the apply kernel instance whose shared-memory attribute is set
+  int* band_items_dev = nullptr;          // device [4*band_nitems]
+  int* band_sync = nullptr;               // device [1 + B*nparts*nwave]: ticket, published items per (chain, part, wavefront)
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
   alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
   alignas(64) unsigned char band_tmap_a[128] = {};  // the same view with narrower boxes: column pieces of the carried block
@@ -204,6 +208,7 @@ int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx*
 int dw_band_chase(Handle* h, Mask mask);
 int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream);
 int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
+void dw_band_apply_items(Handle* h, std::vector<int>& items4);
 
 // generic batched complex GEMM on FP64 tensor cores (gemm_dmma.cu)
 // C = beta*C + alpha * sum_seg opA(A_seg) * opB(B_seg);  opX: 0 = N, 1 = C (conjugate transpose)
