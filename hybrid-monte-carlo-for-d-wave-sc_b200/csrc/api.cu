@@ -177,14 +177,14 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
   if (h->band_b > 0) {
     const size_t nblk = h->band_blk_s0.size();
     AL(h->band_pos, (size_t)n); AL(h->band_prog, nB + (size_t)B); AL(h->band_tau, nB * h->band_KT);
-    AL(h->band_VT, nblk * DW_APPLY_G * DW_APPLY_ROWS * B);
+    AL(h->band_VT, nblk * 2 * DW_APPLY_G * DW_APPLY_ROWS * B);
     AL(h->band_blk_s0_dev, nblk); AL(h->band_blk_k_dev, nblk);
     {
       std::vector<int> items4;
       dw_band_apply_items(h, items4);
       AL(h->band_items_dev, items4.size());
       if ((rc = h2d(h, h->band_items_dev, items4.data(), sizeof(int) * items4.size())) != DWHMC_OK) return fail(rc);
-      AL(h->band_sync, 1 + (size_t)B * h->band_nparts * (h->band_wave_start.size() - 1));
+      AL(h->band_sync, 1 + (size_t)B * (h->band_wave_start.size() - 1));
     }
     if ((rc = h2d(h, h->band_pos, h->band_pos_host.data(), sizeof(int) * n)) != DWHMC_OK) return fail(rc);
     if ((rc = h2d(h, h->band_blk_s0_dev, h->band_blk_s0.data(), sizeof(int) * nblk)) != DWHMC_OK) return fail(rc);

@@ -40,8 +40,9 @@ static_assert(A2_G == DW_APPLY_G && A2_ROWS == DW_APPLY_ROWS, "internal.h");
 
 // ---- T factors ------------------------------------------------------------------------------------------
 // block (s0, k): columns s0 .. s0+g-1 of V, rows rlo = s0+1+kb .. ; column c is non-zero on rows
-// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block; the output is
-// -Vb T, [A2_G reflectors][A2_ROWS rows] per block, zero padded (what band_apply2_kernel keeps in shared memory).
+// [c, c+b) of the block.  T (forward, columnwise) from the Gram matrix of the masked block; the output is what
+// band_apply2_kernel keeps in shared memory, ready for bulk copies: conj(Vb) and -Vb T, each [A2_G reflectors]
+// [A2_ROWS rows] per block, zero padded.
 __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restrict__ Vall, const cplx* __restrict__ tau2,
                                                            cplx* __restrict__ NVTall, const int* __restrict__ blk_s0,
                                                            const int* __restrict__ blk_k, int n, int b, int g, int KT,
@@ -111,11 +112,13 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       }
     }
   }
-  // -Vb T
-  cplx* nvt = NVTall + ((size_t)ch * nblk + blk) * (A2_G * A2_ROWS);
+  // conj(Vb) and -Vb T
+  cplx* cvo = NVTall + ((size_t)ch * nblk + blk) * (2 * A2_G * A2_ROWS);
+  cplx* nvt = cvo + A2_G * A2_ROWS;
   for (int rc = 0; rc < A2_ROWS; rc += 32) {
     __syncthreads();
     load_chunk(rc);
+    if (tid < TG) for (int c = gg; c < TG; ++c) Vs[tid * (TG + 1) + c] = zero;     // columns of a short last group
     __syncthreads();
     for (int idx = tid; idx < 32 * A2_G; idx += 256) {
       const int r = idx & 31, m = idx >> 5;
@@ -124,6 +127,8 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       if (m < gg && rc + r < rows)
         for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
       nvt[m * A2_ROWS + rc + r] = make_double2(-a.x, -a.y);
+      const cplx v = Vs[r * (TG + 1) + m];
+      cvo[m * A2_ROWS + rc + r] = make_double2(v.x, -v.y);
     }
   }
 }
@@ -160,16 +165,36 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 struct Apply2Args {
   cplx* Z; const cplx* V; const cplx* NVT;
   const int* blk_s0; const int* blk_k;
-  const int4* items;             // per chain, wavefront order: (block, column part, wavefront, blocks of the previous wavefront)
-  int item0, item1;              // range of items of this launch (all of them, or one wavefront)
+  const int4* items;             // wavefront order, chains one after the other inside a wavefront: (block, column part |
+                                 // parts << 16, wavefront | chain << 16, items of the chain in the previous wavefront)
+  int nitems;
   int* ticket;                   // [1]
-  int* done;                     // [B][nparts][nwave] published items
+  int* done;                     // [B][nwave] published items
   int* status;                   // [>= 3]: [2] set if a wait timed out
   const int* halfflag;
-  int n, b, g, nblk, B, nparts, nwave, c_lo, use_half;
+  int n, b, g, nblk, B, nwave, c_lo, use_half;
   Mask mask;
 };
 
@@ -183,53 +208,67 @@ __global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
   cplx* CV = reinterpret_cast<cplx*>(smem_apply);    // [A2_G][LDV]  conj(Vb)[r][m] at m * LDV + r
   cplx* NVT = CV + A2_G * LDV;                        // [A2_G][LDV]  -(Vb T)[r][m]
   __shared__ int s_q;
+  __shared__ unsigned long long s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fk = lane & 3;
   const int n = a.n, b = a.b;
   const cplx zero = make_double2(0.0, 0.0);
-  const int total = (a.item1 - a.item0) * a.B;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  unsigned phase = 0;
   for (;;) {
     __syncthreads();                                  // everyone is done with shared memory and s_q
     if (tid == 0) s_q = atomicAdd(a.ticket, 1);
     __syncthreads();
     const int q = s_q;
-    if (q >= total) return;
-    const int chain = q % a.B;
+    if (q >= a.nitems) return;
+    const int4 it = a.items[q];
+    const int blk = it.x, part = it.y & 0xffff, nparts = it.y >> 16, wave = it.z & 0xffff, chain = it.z >> 16;
     if (!a.mask.on(chain)) continue;
-    const int4 it = a.items[a.item0 + q / a.B];
-    const int blk = it.x, part = it.y, wave = it.z;
     const int s0 = a.blk_s0[blk], k = a.blk_k[blk];
     const int gg = min(a.g, n - 1 - s0);
     const int rlo = s0 + 1 + k * b;
     const int rows = min(n - rlo, b + gg - 1);
-    int* done = a.done + ((size_t)chain * a.nparts + part) * a.nwave;
+    int* done = a.done + (size_t)chain * a.nwave;
     const int cstart = (a.use_half && a.halfflag[chain] != 0) ? a.c_lo : 0;
     const int nstrip = (n - cstart + 7) >> 3;
-    const int per = (nstrip + a.nparts - 1) / a.nparts;
+    const int per = (nstrip + nparts - 1) / nparts;
     const int st0 = part * per, st1 = min(nstrip, st0 + per);
     if (rows > 0 && gg > 0 && st0 < st1) {
-      // the blocks of the previous wavefront of this (chain, column part) have to be in global memory
-      if (tid == 0 && wave > 0 && it.w > 0) {
-        int spins = 0;
-        while (ld_acquire(done + wave - 1) < it.w) {
-          __nanosleep(64);
-          if (++spins > (1 << 22)) { atomicExch(a.status + 2, 1); break; }
+      if (tid == 0) {
+        // conj(Vb) and -Vb T by the bulk-copy engine, one copy per reflector (the rows of shared memory are padded)
+        const cplx* src = a.NVT + ((size_t)chain * a.nblk + blk) * (2 * A2_G * A2_ROWS);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // reads of the previous item -> bulk writes
+        mbar_expect_tx(&s_bar, (unsigned)(2 * A2_G * ROWS * sizeof(cplx)));
+        for (int m = 0; m < A2_G; ++m) {
+          bulk_g2s(CV + m * LDV, src + m * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
+          bulk_g2s(NVT + m * LDV, src + (A2_G + m) * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
+        }
+        // the blocks of the previous wavefront of this chain have to be in global memory
+        if (wave > 0 && it.w > 0) {
+          int spins = 0;
+          while (ld_acquire(done + wave - 1) < it.w) {
+            __nanosleep(64);
+            if (++spins > (1 << 22)) { atomicExch(a.status + 2, 1); break; }
+          }
         }
       }
-      const cplx* V = a.V + (size_t)chain * n * n;
-      const cplx* nvt = a.NVT + ((size_t)chain * a.nblk + blk) * (A2_G * A2_ROWS);
-      for (int idx = tid; idx < A2_G * ROWS; idx += A2_TH) {
-        const int r = idx % ROWS, m = idx / ROWS;
-        const bool ok = m < gg && r < rows && r - m >= 0 && r - m < b;
-        const cplx v = ok ? V[(size_t)(s0 + m) * n + rlo + r] : zero;
-        CV[m * LDV + r] = make_double2(v.x, -v.y);
-        NVT[m * LDV + r] = nvt[m * A2_ROWS + r];
-      }
       __syncthreads();
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
       for (int strip = st0 + warp; strip < st1; strip += A2_WARPS) {
         const int col = cstart + strip * 8 + fr;
         const bool colok = col < n;
         cplx* zc = a.Z + ((size_t)chain * n + (colok ? col : 0)) * n + rlo + 2 * fk;
+        if (strip + A2_WARPS < st1) {
+          // next strip of this warp -> L2 while this one is being worked on (lane = 128-byte line of a column)
+          const int pcol = col + 8 * A2_WARPS;
+          if (pcol < n) {
+            const char* pz = reinterpret_cast<const char*>(a.Z + ((size_t)chain * n + pcol) * n + rlo);
+            for (int off = fk * 128; off < rows * (int)sizeof(cplx); off += 4 * 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + off));
+          }
+        }
         double zr[NRT][2], zi[NRT][2];
 #pragma unroll
         for (int rt = 0; rt < NRT; ++rt) {
@@ -322,22 +361,33 @@ int dw_band_tfactors(Handle* h, Mask mask, cudaStream_t stream) {
   return DWHMC_OK;
 }
 
-// item list of the back-transformation (per chain): wavefront order, (block, column part, wavefront, blocks of the
-// previous wavefront); called once from dwhmc_create after dw_band_setup
+// item list of the back-transformation: wavefront order, inside a wavefront the chains one after the other (the items
+// a chain's next wavefront waits for are then the ones handed out longest ago); called once from dwhmc_create after
+// dw_band_setup.  Column parts (strips of 8 columns, at least one per warp): one part per block wherever the blocks of a
+// wavefront fill the GPU on their own, more parts in the thin wavefronts at both ends.
 void dw_band_apply_items(Handle* h, std::vector<int>& items4) {
   const int n = h->n;
   const int nwave = (int)h->band_wave_start.size() - 1;
-  // column parts: strips of 8 columns, about 24 per part (three per warp) on the half spectrum
   const int nstrip = (n - (h->N / 16) * 16 + 7) / 8;
-  h->band_nparts = std::max(1, std::min(4, (nstrip + 12) / 24));
+  const int maxparts = std::max(1, (nstrip + A2_WARPS - 1) / A2_WARPS);
+  int force = 0;
+  if (const char* e = getenv("DWHMC_APPLY_PARTS")) force = atoi(e);
   items4.clear();
+  int prev = 0;
   for (int t = 0; t < nwave; ++t) {
     const int w0 = h->band_wave_start[t], w1 = h->band_wave_start[t + 1];
-    const int prev = t > 0 ? h->band_wave_start[t] - h->band_wave_start[t - 1] : 0;
-    for (int i = w0; i < w1; ++i)
-      for (int p = 0; p < h->band_nparts; ++p) {
-        items4.push_back(h->band_wave_blk[i]); items4.push_back(p); items4.push_back(t); items4.push_back(prev);
-      }
+    const int nsub = w1 - w0;
+    if (nsub <= 0) continue;
+    int np = (13 * h->nsm + 10 * nsub * h->B - 1) / (10 * nsub * h->B);
+    if (force > 0) np = force;
+    np = std::max(1, std::min(np, maxparts));
+    for (int c = 0; c < h->B; ++c)
+      for (int i = w0; i < w1; ++i)
+        for (int p = 0; p < np; ++p) {
+          items4.push_back(h->band_wave_blk[i]); items4.push_back(p | (np << 16)); items4.push_back(t | (c << 16));
+          items4.push_back(prev);
+        }
+    prev = nsub * np;
   }
   h->band_nitems = (int)items4.size() / 4;
 }
@@ -369,25 +419,14 @@ int dw_band_backtransform(Handle* h, cplx* U, Mask mask, bool ph) {
   a.Z = Z; a.V = h->V; a.NVT = h->band_VT; a.blk_s0 = h->band_blk_s0_dev; a.blk_k = h->band_blk_k_dev;
   a.items = reinterpret_cast<const int4*>(h->band_items_dev);
   a.ticket = h->band_sync; a.done = h->band_sync + 1; a.status = h->status; a.halfflag = h->halfflag;
-  a.n = n; a.b = h->band_b; a.g = h->band_g; a.nblk = (int)h->band_blk_s0.size(); a.B = B; a.nparts = h->band_nparts;
+  a.n = n; a.b = h->band_b; a.g = h->band_g; a.nblk = (int)h->band_blk_s0.size(); a.B = B;
   a.nwave = nwave; a.c_lo = c_lo; a.use_half = half ? 1 : 0; a.mask = mask;
-  const size_t nsync = 1 + (size_t)B * h->band_nparts * nwave;
+  const size_t nsync = 1 + (size_t)B * nwave;
   DW_CUDA(h, cudaMemsetAsync(h->band_sync, 0, sizeof(int) * nsync, h->stream));
-  static const bool per_wave = getenv("DWHMC_APPLY_WAVES") != nullptr;     // debugging: one launch per wavefront
-  if (!per_wave) {
-    a.item0 = 0; a.item1 = h->band_nitems;
-    const int ctas = std::min(h->nsm, std::max(1, a.item1 * B));
-    kern<<<ctas, A2_TH, smem, h->stream>>>(a);
-    DW_LAUNCH_CHECK(h);
-  } else {
-    for (int t = 0; t < nwave; ++t) {
-      a.item0 = h->band_wave_start[t] * h->band_nparts; a.item1 = h->band_wave_start[t + 1] * h->band_nparts;
-      if (a.item1 <= a.item0) continue;
-      DW_CUDA(h, cudaMemsetAsync(h->band_sync, 0, sizeof(int), h->stream));
-      kern<<<std::min(h->nsm, (a.item1 - a.item0) * B), A2_TH, smem, h->stream>>>(a);
-      DW_LAUNCH_CHECK(h);
-    }
-  }
+  a.nitems = h->band_nitems;
+  const int ctas = std::min(h->nsm, std::max(1, a.nitems));
+  kern<<<ctas, A2_TH, smem, h->stream>>>(a);
+  DW_LAUNCH_CHECK(h);
   {
     dim3 grid(n, B);
     band_unpermute_kernel<<<grid, 256, 0, h->stream>>>(Z, U, h->band_pos, h->halfflag, c_lo, n, mask);

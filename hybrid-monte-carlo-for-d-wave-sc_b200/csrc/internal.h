@@ -132,11 +132,11 @@ struct Handle {
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
-  cplx* band_VT = nullptr;      // device [nblk*DW_APPLY_G*DW_APPLY_ROWS*B]: -V T per block of the back-transformation
-  int band_nparts = 1, band_nitems = 0;   // column parts per block; work items per chain (blocks x parts, wavefront order)
+  cplx* band_VT = nullptr;      // device [nblk*2*DW_APPLY_G*DW_APPLY_ROWS*B]: conj(V) and -V T per block of the back-transformation
+  int band_nitems = 0;                    // work items per chain of the back-transformation (blocks x column parts, wavefront order)
   int band_apply_attr = 0;                // row tiles of the apply kernel instance whose shared-memory attribute is set
   int* band_items_dev = nullptr;          // device [4*band_nitems]
-  int* band_sync = nullptr;               // device [1 + B*nparts*nwave]: ticket, published items per (chain, part, wavefront)
+  int* band_sync = nullptr;               // device [1 + B*nwave]: ticket, published items per (chain, wavefront)
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
   alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
   alignas(64) unsigned char band_tmap_a[128] = {};  // the same view with narrower boxes: column pieces of the carried block
