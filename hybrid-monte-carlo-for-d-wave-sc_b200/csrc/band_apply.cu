@@ -2,7 +2,8 @@
 // the eigenvectors eigen! returns).  Q2 is the product of the Householder reflectors of the bulge chase (band.cu);
 // the reflectors of g consecutive sweeps at the same step form one staircase block reflector I - Vb T Vb^H.
 //   band_tfactor_kernel   T and Vb T per block (runs beside the D&C stage)
-//   band_apply2_kernel    the block reflectors on the FP64 tensor cores, Z strips held in registers
+//   band_apply2_kernel    the block reflectors on the FP64 tensor cores, Z strips held in registers, three real
+//                         products per complex one
 //   band_unpermute_kernel rows back to the reference's site order
 #include <algorithm>
 #include <cstdio>
@@ -33,8 +34,22 @@ constexpr int A2_NRT = 17;               // tiles of 8 rows: blocks of up to 136
 constexpr int A2_ROWS = 8 * A2_NRT;
 constexpr int A2_WARPS = 8;              // 255 registers per thread: the whole row range of a strip lives in registers
 constexpr int A2_TH = 32 * A2_WARPS;
-// odd leading dimension 8 NRT + 1: both operand read patterns are conflict-free
-constexpr size_t apply2_smem(int nrt) { return sizeof(cplx) * 2 * (size_t)A2_G * (8 * nrt + 1); }
+// Complex products are formed from three real ones (a + ib)(c + id): k1 = (a + b) c, k2 = a (d - c), k3 = b (c + d),
+// re = k1 - k3, im = k1 + k2; the shared-memory operands are stored as (c, d - c) pairs plus a plane of c + d.
+constexpr int A2_LDT = A2_G + 8;         // row length of the transposed c + d plane of -Vb T (= 8 mod 16: conflict-free pairs)
+// per block in global memory (band_tfactor_kernel -> band_apply2_kernel), in doubles
+constexpr size_t A2_OFF_CVX = 0;                                      // [A2_G][A2_ROWS] (c, d - c) of conj(Vb)
+constexpr size_t A2_OFF_NTX = A2_OFF_CVX + 2 * (size_t)A2_G * A2_ROWS;  // [A2_G][A2_ROWS] (c, d - c) of -Vb T
+constexpr size_t A2_OFF_CVS = A2_OFF_NTX + 2 * (size_t)A2_G * A2_ROWS;  // [A2_G][A2_ROWS] c + d of conj(Vb)
+constexpr size_t A2_OFF_NTS = A2_OFF_CVS + (size_t)A2_G * A2_ROWS;      // [A2_ROWS][A2_LDT] c + d of -Vb T, transposed
+constexpr size_t A2_BLOCK_DOUBLES = A2_OFF_NTS + (size_t)A2_ROWS * A2_LDT;
+static_assert(A2_BLOCK_DOUBLES == DW_APPLY_BLOCK_DOUBLES, "internal.h");
+// shared memory: pair planes with odd leading dimension 8 NRT + 1 (both operand read patterns conflict-free), the
+// c + d plane of conj(Vb) with rows of 8 NRT (+ 8 if that is a multiple of 16) doubles, the one of -Vb T as in global memory
+__host__ __device__ constexpr int apply2_lds(int nrt) { return (8 * nrt) % 16 == 8 ? 8 * nrt : 8 * nrt + 8; }
+constexpr size_t apply2_smem(int nrt) {
+  return sizeof(cplx) * 2 * (size_t)A2_G * (8 * nrt + 1) + sizeof(double) * ((size_t)A2_G * apply2_lds(nrt) + (size_t)8 * nrt * A2_LDT);
+}
 
 static_assert(A2_G == DW_APPLY_G && A2_ROWS == DW_APPLY_ROWS, "internal.h");
 
@@ -112,9 +127,12 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       }
     }
   }
-  // conj(Vb) and -Vb T
-  cplx* cvo = NVTall + ((size_t)ch * nblk + blk) * (2 * A2_G * A2_ROWS);
-  cplx* nvt = cvo + A2_G * A2_ROWS;
+  // conj(Vb) and -Vb T as (c, d - c) pairs and c + d planes
+  double* ob = reinterpret_cast<double*>(NVTall) + ((size_t)ch * nblk + blk) * A2_BLOCK_DOUBLES;
+  cplx* cvx = reinterpret_cast<cplx*>(ob + A2_OFF_CVX);
+  cplx* ntx = reinterpret_cast<cplx*>(ob + A2_OFF_NTX);
+  double* cvs = ob + A2_OFF_CVS;
+  double* nts = ob + A2_OFF_NTS;
   for (int rc = 0; rc < A2_ROWS; rc += 32) {
     __syncthreads();
     load_chunk(rc);
@@ -126,9 +144,11 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       cplx a = zero;
       if (m < gg && rc + r < rows)
         for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
-      nvt[m * A2_ROWS + rc + r] = make_double2(-a.x, -a.y);
+      ntx[m * A2_ROWS + rc + r] = make_double2(-a.x, a.x - a.y);
+      nts[(rc + r) * A2_LDT + m] = -a.x - a.y;
       const cplx v = Vs[r * (TG + 1) + m];
-      cvo[m * A2_ROWS + rc + r] = make_double2(v.x, -v.y);
+      cvx[m * A2_ROWS + rc + r] = make_double2(v.x, -v.y - v.x);
+      cvs[m * A2_ROWS + rc + r] = v.x - v.y;
     }
   }
 }
@@ -203,10 +223,12 @@ struct Apply2Args {
 // (>= (b + 6) / 8) or rt < mt are skipped at compile time; partial blocks at the matrix end are zero padded.
 template <int NRT>
 __global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
-  constexpr int ROWS = 8 * NRT, LDV = ROWS + 1, SK = NRT - 4;
+  constexpr int ROWS = 8 * NRT, LDV = ROWS + 1, LDS = apply2_lds(NRT), SK = NRT - 4;
   extern __shared__ __align__(16) unsigned char smem_apply[];
-  cplx* CV = reinterpret_cast<cplx*>(smem_apply);    // [A2_G][LDV]  conj(Vb)[r][m] at m * LDV + r
-  cplx* NVT = CV + A2_G * LDV;                        // [A2_G][LDV]  -(Vb T)[r][m]
+  cplx* CV = reinterpret_cast<cplx*>(smem_apply);    // [A2_G][LDV]  (c, d - c) of conj(Vb)[r][m] at m * LDV + r
+  cplx* NVT = CV + A2_G * LDV;                        // [A2_G][LDV]  (c, d - c) of -(Vb T)[r][m]
+  double* CVS = reinterpret_cast<double*>(NVT + A2_G * LDV);   // [A2_G][LDS]    c + d of conj(Vb)[r][m] at m * LDS + r
+  double* NTS = CVS + A2_G * LDS;                               // [ROWS][A2_LDT] c + d of -(Vb T)[r][m] at r * A2_LDT + m
   __shared__ int s_q;
   __shared__ unsigned long long s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -236,14 +258,18 @@ __global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
     const int st0 = part * per, st1 = min(nstrip, st0 + per);
     if (rows > 0 && gg > 0 && st0 < st1) {
       if (tid == 0) {
-        // conj(Vb) and -Vb T by the bulk-copy engine, one copy per reflector (the rows of shared memory are padded)
-        const cplx* src = a.NVT + ((size_t)chain * a.nblk + blk) * (2 * A2_G * A2_ROWS);
+        // operands by the bulk-copy engine, one copy per reflector (the rows of shared memory are padded)
+        const double* src = reinterpret_cast<const double*>(a.NVT) + ((size_t)chain * a.nblk + blk) * A2_BLOCK_DOUBLES;
+        const cplx* scv = reinterpret_cast<const cplx*>(src + A2_OFF_CVX);
+        const cplx* snt = reinterpret_cast<const cplx*>(src + A2_OFF_NTX);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // reads of the previous item -> bulk writes
-        mbar_expect_tx(&s_bar, (unsigned)(2 * A2_G * ROWS * sizeof(cplx)));
+        mbar_expect_tx(&s_bar, (unsigned)(2 * A2_G * ROWS * sizeof(cplx) + (A2_G * ROWS + ROWS * A2_LDT) * sizeof(double)));
         for (int m = 0; m < A2_G; ++m) {
-          bulk_g2s(CV + m * LDV, src + m * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
-          bulk_g2s(NVT + m * LDV, src + (A2_G + m) * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
+          bulk_g2s(CV + m * LDV, scv + m * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
+          bulk_g2s(NVT + m * LDV, snt + m * A2_ROWS, (unsigned)(ROWS * sizeof(cplx)), &s_bar);
+          bulk_g2s(CVS + m * LDS, src + A2_OFF_CVS + m * A2_ROWS, (unsigned)(ROWS * sizeof(double)), &s_bar);
         }
+        bulk_g2s(NTS, src + A2_OFF_NTS, (unsigned)(ROWS * A2_LDT * sizeof(double)), &s_bar);
         // the blocks of the previous wavefront of this chain have to be in global memory
         if (wave > 0 && it.w > 0) {
           int spins = 0;
@@ -256,20 +282,29 @@ __global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
       __syncthreads();
       mbar_wait(&s_bar, phase);
       phase ^= 1;
-      for (int strip = st0 + warp; strip < st1; strip += A2_WARPS) {
-        const int col = cstart + strip * 8 + fr;
-        const bool colok = col < n;
-        cplx* zc = a.Z + ((size_t)chain * n + (colok ? col : 0)) * n + rlo + 2 * fk;
-        if (strip + A2_WARPS < st1) {
-          // next strip of this warp -> L2 while this one is being worked on (lane = 128-byte line of a column)
-          const int pcol = col + 8 * A2_WARPS;
-          if (pcol < n) {
-            const char* pz = reinterpret_cast<const char*>(a.Z + ((size_t)chain * n + pcol) * n + rlo);
-            for (int off = fk * 128; off < rows * (int)sizeof(cplx); off += 4 * 128)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + off));
-          }
+      // Strips of this warp.  The row tiles of the next strip are loaded into the registers of the current one as
+      // soon as their final values have been stored (inside the second product), so the loads and stores of a strip
+      // are spread over the tensor work instead of forming a burst before and after it.
+      double zr[NRT][2], zi[NRT][2];
+      int strip = st0 + warp;
+      auto strip_ptr = [&](int st, bool& cok) -> cplx* {
+        const int col = cstart + st * 8 + fr;
+        cok = col < n;
+        return a.Z + ((size_t)chain * n + (cok ? col : 0)) * n + rlo + 2 * fk;
+      };
+      auto prefetch_strip = [&](int st) {              // -> L2 (lane = 128-byte lines of a column)
+        const int col = cstart + st * 8 + fr;
+        if (st < st1 && col < n) {
+          const char* pz = reinterpret_cast<const char*>(a.Z + ((size_t)chain * n + col) * n + rlo);
+          for (int off = fk * 128; off < rows * (int)sizeof(cplx); off += 4 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pz + off));
         }
-        double zr[NRT][2], zi[NRT][2];
+      };
+      bool colok = false;
+      cplx* zc = nullptr;
+      if (strip < st1) {
+        zc = strip_ptr(strip, colok);
+        prefetch_strip(strip + A2_WARPS);
 #pragma unroll
         for (int rt = 0; rt < NRT; ++rt) {
 #pragma unroll
@@ -279,48 +314,68 @@ __global__ void __launch_bounds__(A2_TH, 1) band_apply2_kernel(Apply2Args a) {
             zr[rt][e] = v.x; zi[rt][e] = v.y;
           }
         }
-        // ---- W^T = Z^T conj(Vb): accumulator (column fr, reflectors 8 mt + 2 fk + {0, 1})
-        double wr[A2_MT][2], wi[A2_MT][2];
+      }
+      while (strip < st1) {
+        const int nxt = strip + A2_WARPS;
+        const bool more = nxt < st1;
+        bool colok_n = false;
+        cplx* zn = more ? strip_ptr(nxt, colok_n) : zc;
+        prefetch_strip(nxt + A2_WARPS);
+        // ---- W^T = Z^T conj(Vb): accumulators (column fr, reflectors 8 mt + 2 fk + {0, 1}) of the three real products
+        double k1[A2_MT][2], k2[A2_MT][2], k3[A2_MT][2];
 #pragma unroll
-        for (int mt = 0; mt < A2_MT; ++mt) { wr[mt][0] = wr[mt][1] = wi[mt][0] = wi[mt][1] = 0.0; }
+        for (int mt = 0; mt < A2_MT; ++mt) { k1[mt][0] = k1[mt][1] = k2[mt][0] = k2[mt][1] = k3[mt][0] = k3[mt][1] = 0.0; }
 #pragma unroll
         for (int rt = 0; rt < NRT; ++rt) {
+          const double as0 = zr[rt][0] + zi[rt][0], as1 = zr[rt][1] + zi[rt][1];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double ar = zr[rt][e], ai = zi[rt][e], nai = dneg(ai);
-#pragma unroll
-            for (int mt = 0; mt < A2_MT; ++mt) {
-              if (rt < mt || rt - mt > SK) continue;
-              const cplx cv = CV[(8 * mt + fr) * LDV + 8 * rt + 2 * fk + e];
-              dmma(wr[mt][0], wr[mt][1], ar, cv.x);
-              dmma(wi[mt][0], wi[mt][1], ar, cv.y);
-              dmma(wr[mt][0], wr[mt][1], nai, cv.y);
-              dmma(wi[mt][0], wi[mt][1], ai, cv.x);
-            }
+          for (int mt = 0; mt < A2_MT; ++mt) {
+            if (rt < mt || rt - mt > SK) continue;
+            const cplx x0 = CV[(8 * mt + fr) * LDV + 8 * rt + 2 * fk];
+            const cplx x1 = CV[(8 * mt + fr) * LDV + 8 * rt + 2 * fk + 1];
+            const double2 sp = *reinterpret_cast<const double2*>(CVS + (8 * mt + fr) * LDS + 8 * rt + 2 * fk);
+            dmma(k1[mt][0], k1[mt][1], as0, x0.x);
+            dmma(k2[mt][0], k2[mt][1], zr[rt][0], x0.y);
+            dmma(k3[mt][0], k3[mt][1], zi[rt][0], sp.x);
+            dmma(k1[mt][0], k1[mt][1], as1, x1.x);
+            dmma(k2[mt][0], k2[mt][1], zr[rt][1], x1.y);
+            dmma(k3[mt][0], k3[mt][1], zi[rt][1], sp.y);
           }
         }
+        // W^T = (k1 - k3) + i (k1 + k2); operands of the second product: real part, imaginary part and their sum
+#pragma unroll
+        for (int mt = 0; mt < A2_MT; ++mt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double re = k1[mt][e] - k3[mt][e], im = k1[mt][e] + k2[mt][e];
+            k1[mt][e] = re + im; k2[mt][e] = re; k3[mt][e] = im;
+          }
         // ---- Z^T += W^T (-Vb T)^T: columns of -Vb T 8 mt .. 8 mt + 7 are non-zero on rows 0 .. 8 mt + 6 + b
 #pragma unroll
         for (int rt = 0; rt < NRT; ++rt) {
+          double p1[2] = {0.0, 0.0}, p2[2] = {0.0, 0.0}, p3[2] = {0.0, 0.0};
 #pragma unroll
           for (int mt = 0; mt < A2_MT; ++mt) {
             if (rt - mt > SK) continue;
+            const cplx x0 = NVT[(8 * mt + 2 * fk) * LDV + 8 * rt + fr];
+            const cplx x1 = NVT[(8 * mt + 2 * fk + 1) * LDV + 8 * rt + fr];
+            const double2 sp = *reinterpret_cast<const double2*>(NTS + (8 * rt + fr) * A2_LDT + 8 * mt + 2 * fk);
+            dmma(p1[0], p1[1], k1[mt][0], x0.x);
+            dmma(p2[0], p2[1], k2[mt][0], x0.y);
+            dmma(p3[0], p3[1], k3[mt][0], sp.x);
+            dmma(p1[0], p1[1], k1[mt][1], x1.x);
+            dmma(p2[0], p2[1], k2[mt][1], x1.y);
+            dmma(p3[0], p3[1], k3[mt][1], sp.y);
+          }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const cplx t = NVT[(8 * mt + 2 * fk + e) * LDV + 8 * rt + fr];
-              dmma(zr[rt][0], zr[rt][1], wr[mt][e], t.x);
-              dmma(zi[rt][0], zi[rt][1], wr[mt][e], t.y);
-              dmma(zr[rt][0], zr[rt][1], dneg(wi[mt][e]), t.y);
-              dmma(zi[rt][0], zi[rt][1], wi[mt][e], t.x);
-            }
+          for (int e = 0; e < 2; ++e) {
+            const bool rok = 8 * rt + 2 * fk + e < rows;
+            if (colok && rok) zc[8 * rt + e] = make_double2(zr[rt][e] + (p1[e] - p3[e]), zi[rt][e] + (p1[e] + p2[e]));
+            const cplx v = (more && colok_n && rok) ? ldcg(zn + 8 * rt + e) : zero;     // same tile of the next strip
+            zr[rt][e] = v.x; zi[rt][e] = v.y;
           }
         }
-#pragma unroll
-        for (int rt = 0; rt < NRT; ++rt) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (colok && 8 * rt + 2 * fk + e < rows) zc[8 * rt + e] = make_double2(zr[rt][e], zi[rt][e]);
-        }
+        strip = nxt; zc = zn; colok = colok_n;
       }
     }
     // publish: every thread's stores are ordered before the counter update

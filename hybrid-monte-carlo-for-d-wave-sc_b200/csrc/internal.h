@@ -24,6 +24,7 @@
 #define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
 #define DW_APPLY_G 32      // reflectors per staircase block of the band route's back-transformation
 #define DW_APPLY_ROWS 136  // rows of such a block (half-bandwidth + DW_APPLY_G - 1 at most)
+#define DW_APPLY_BLOCK_DOUBLES (2 * 2 * DW_APPLY_G * DW_APPLY_ROWS + DW_APPLY_G * DW_APPLY_ROWS + DW_APPLY_ROWS * (DW_APPLY_G + 8))  // operand planes per block
 #define DW_FCHUNK 32      // eigenvector columns per CTA in the bond-correlator kernel
 
 typedef double2 cplx;
@@ -132,7 +133,7 @@ struct Handle {
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
-  cplx* band_VT = nullptr;      // device [nblk*2*DW_APPLY_G*DW_APPLY_ROWS*B]: conj(V) and -V T per block of the back-transformation
+  cplx* band_VT = nullptr;      // device, DW_APPLY_BLOCK_DOUBLES doubles per (chain, block): conj(V) and -V T, operand planes of the back-transformation
   int band_nitems = 0;                    // work items per chain of the back-transformation (blocks x column parts, wavefront order)
   int band_apply_attr = 0;                // row tiles of the apply kernel instance whose shared-memory attribute is set
   int* band_items_dev = nullptr;          // device [4*band_nitems]
