@@ -57,6 +57,11 @@ static int check_status(Handle* h) {
     cudaMemsetAsync(h->status, 0, sizeof(int) * 4, h->stream);
     return DWHMC_E_NOCONV;
   }
+  if (st[2]) {
+    h->err = "band route: a wait on another CTA's progress timed out (results invalid)";
+    cudaMemsetAsync(h->status, 0, sizeof(int) * 4, h->stream);
+    return DWHMC_E_CUDA;
+  }
   return DWHMC_OK;
 }
 
@@ -268,10 +273,10 @@ int dwhmc_set_params(dwhmc_handle hh, const double* t, const double* tp, const d
   if (!t || !tp || !mu || !beta || !J || !mass) BADARG("dwhmc_set_params: NULL array");
   const int B = h->B;
   const double* src[6] = {t, tp, mu, beta, J, mass};
+  for (int b = 0; b < B; ++b)                       // validate before touching the host mirror
+    if (!(J[b] != 0.0) || !(mass[b] != 0.0)) BADARG("dwhmc_set_params: J and mass must be nonzero");
   for (int k = 0; k < 6; ++k)
     for (int b = 0; b < B; ++b) h->h_par[(size_t)k * B + b] = src[k][b];
-  for (int b = 0; b < B; ++b)
-    if (!(J[b] != 0.0) || !(mass[b] != 0.0)) BADARG("dwhmc_set_params: J and mass must be nonzero");
   h->params_set = true;
   return h2d(h, h->par, h->h_par.data(), sizeof(double) * 6 * B);
 }
@@ -499,13 +504,24 @@ int dwhmc_trajectory(dwhmc_handle hh, const int32_t* Nt, const double* dt, const
   int max_nt = 0;
   DW_TRY(load_steps(h, Nt, dt, &max_nt));
   if (pi0) DW_TRY(h2d(h, h->pi, pi0, sizeof(cplx) * (size_t)h->n * h->B));
-  DW_TRY(trajectory_enqueue(h, max_nt, pi0 == nullptr));
-  h->pending = true;
-  if (H_old) DW_TRY(d2h(h, H_old, h->Hold_dev, sizeof(double) * h->B));
-  if (H_new) DW_TRY(d2h(h, H_new, h->Hnew_dev, sizeof(double) * h->B));
-  if (dH) DW_TRY(d2h(h, dH, h->dH_dev, sizeof(double) * h->B));
-  DW_CUDA(h, cudaStreamSynchronize(h->stream));
-  return check_status(h);
+  // On any failure after the trajectory has been enqueued the proposal is dropped: Delta goes back to the backup
+  // and the handle stays usable, like the reference's cache after a LAPACKException (src/Hamiltonian.jl:106).
+  auto run = [&]() -> int {
+    DW_TRY(trajectory_enqueue(h, max_nt, pi0 == nullptr));
+    if (H_old) DW_TRY(d2h(h, H_old, h->Hold_dev, sizeof(double) * h->B));
+    if (H_new) DW_TRY(d2h(h, H_new, h->Hnew_dev, sizeof(double) * h->B));
+    if (dH) DW_TRY(d2h(h, dH, h->dH_dev, sizeof(double) * h->B));
+    DW_CUDA(h, cudaStreamSynchronize(h->stream));
+    return check_status(h);
+  };
+  const int rc = run();
+  if (rc == DWHMC_OK) { h->pending = true; return DWHMC_OK; }
+  const std::string why = h->err;
+  if (cudaMemsetAsync(h->accept_dev, 0, sizeof(int) * h->B, h->stream) == cudaSuccess && dw_commit_dev(h) == DWHMC_OK)
+    cudaStreamSynchronize(h->stream);
+  h->pending = false;
+  h->err = why;
+  return rc;
 }
 
 int dwhmc_commit(dwhmc_handle hh, const int32_t* accept) {

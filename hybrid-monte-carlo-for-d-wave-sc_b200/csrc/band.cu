@@ -142,6 +142,7 @@ struct ChaseArgs {
   int n, b, LD, KT, P, c0;       // c0: first chain of this launch
   int* next; int B, stride;      // helper-warp kernel: per-chain sweep tickets, chains, rotation stride of the spare CTAs
   int nsweep;                    // sweeps handed out by tickets (the rest is left to chase_tail_kernel)
+  int* status;                   // device status words: [2] set when a progress wait timed out
   Mask mask;
   long long* clk;                // optional [8] phase clock accumulators of CTA 0 (profiling experiments)
 };
@@ -249,7 +250,11 @@ __global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
       if (s > 0) {
         if (tid == 0) {
           const int need = k + 3;
-          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
+          int spins = 0;                               // bounded: a lost neighbour ends in an error code, not a hang
+          while (ld_acquire(prog + s - 1) < need) {
+            __nanosleep(32);
+            if (++spins > (1 << 24)) { atomicExch(g.status + 2, 1); break; }
+          }
         }
         __syncthreads();
       }
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
   cplx* part = wc + TB;                              // [NP][LDP]
   cplx* red = part + NP * LDP;                       // [32]
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
-  int* sw = reinterpret_cast<int*>(bar + 1);         // [2] chain and sweep of the ticket just taken (-1: none left)
+  volatile int* sw = reinterpret_cast<volatile int*>(bar + 1);   // [3] chain and sweep of the ticket just taken (-1: none left), spin count
   const int tid = threadIdx.x;
   if (tid == 0) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -886,7 +891,11 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
         if (l0) {
           if (s > 0) {
             const int need = k + 2;
-            while (ld_acquire(prog + s - 1) < need) __nanosleep(20);
+            sw[2] = 0;                                 // spin count (in shared memory: the kernel has no register to spare);
+            while (ld_acquire(prog + s - 1) < need) {  // bounded: a lost neighbour ends in an error code, not a hang
+              __nanosleep(20);
+              if (++sw[2] > (1 << 24)) { atomicExch(g.status + 2, 1); break; }
+            }
           }
           if (k > 0) {
             // the corner element is fetched while the last piece of the block is still landing
@@ -1567,7 +1576,7 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
     ChaseArgs a;
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
     a.n = n; a.b = bw; a.LD = h->band_LD; a.KT = h->band_KT; a.P = P; a.c0 = c0; a.mask = mask;
-    a.next = h->band_prog + (size_t)n * B; a.B = B; a.stride = 1;
+    a.next = h->band_prog + (size_t)n * B; a.B = B; a.stride = 1; a.status = h->status;
     static const bool no_tail = getenv("DWHMC_BAND_NOTAIL") != nullptr;
     const bool tail = tickets && !no_tail && n - 1 - bw >= 1;
     a.nsweep = tail ? n - 1 - bw : n - 1;
