@@ -168,7 +168,7 @@ def test_clean_limit_bcs_gap_equation(dw):
     dt_me = math.pi * math.sqrt(PHYS["mass"] * J / beta) / 5
     cb.run_sweeps(50, 20, dt_th)
     nacc, _, obs = cb.run_sweeps(100, 5, dt_me, observables=True)        # obs [sweep, chain, 9]
-    dglob = obs[:, :, 2]                                                  # Delta_global, src/Observables.jl:108-112
+    dglob = obs[:, :, 3]                                                  # Delta_global (ObservablesResult field 4, src/Observables.jl:70-80)
     assert np.all(nacc > 10)                                              # the chains move
     for b in range(B):
         m = float(np.mean(dglob[:, b]))
