@@ -119,7 +119,6 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     if (v >= 1 && v <= DW_NGROUP) h->ngroups = v;
   }
   if (const char* ep = getenv("DWHMC_PH")) h->ph_mode = atoi(ep) ? 1 : 0;
-  if (const char* ev = getenv("DWHMC_HEMV")) h->hemv_variant = atoi(ev);
   cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device);
   auto fail = [&](int rc) { g_create_err = h->err; dwhmc_destroy(hs); return rc; };
   if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(DWHMC_E_CUDA); }

@@ -8,18 +8,15 @@
 //   chase           band -> real tridiagonal by Householder bulge chasing (Lang's algorithm):
 //                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; persistent CTAs, one sweep
 //                   each at a time, sweeps of a chain pipelined through release/acquire progress
-//                   counters (two steps apart in the TMA kernels, three in the generic chase_kernel);
+//                   counters (two steps apart in the TMA kernel, three in the generic chase_kernel);
 //                   the block pushed out by a step stays in shared memory for the next one (3 b^2
 //                   elements of global traffic per step).  chase_tmah_kernel<b, ...> (compile-time b,
 //                   the default): TMA tensor copies in column pieces, a helper warp for everything that
-//                   waits on the memory system, sweeps handed out by ticket counters to one CTA per SM;
-//                   chase_tma_kernel<b, ...>: its predecessor without helper warp (DWHMC_BAND_HELPER=0);
-//                   chase_kernel handles any b <= 101.
-//   tfactor + back-transformation   U = Q2 Z: reflectors of g consecutive sweeps at the same step
-//                   form one staircase block reflector; band_apply_kernel applies a wavefront of
-//                   independent blocks per launch on the FP64 tensor cores (fallback: three DMMA
-//                   GEMMs per block through gemm_dmma.cu)
-//   unpermute       rows back to the reference's site order
+//                   waits on the memory system, sweeps handed out by ticket counters to one CTA per SM,
+//                   the last b sweeps in chase_tail_kernel; chase_kernel (any b <= 101, load/store units)
+//                   is the one fallback (DWHMC_BAND_GENERIC=1).
+// The back-transformation U = Q2 Z (T factors, block reflectors on the FP64 tensor cores, rows back to the
+// reference's site order) is in band_apply.cu.
 // The numerics (LAPACK-style zlarfg / zhetd2 updates, application order of the blocks) are the
 // ones prototyped against LAPACK in tests/algo_proto_band.py.
 #include <cooperative_groups.h>
@@ -450,15 +447,14 @@ __global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
 }
 
 // ---- TMA chase kernel for a compile-time half-bandwidth ----------------------------------------------------
-// Same algorithm and data flow as chase_kernel.  The b x b blocks are covered exactly by a TR x TC thread grid
-// with an RB x CB sub-block per thread (TR RB = TC CB = TB), so every offset is a compile-time constant off one
-// per-thread base and the products run on register operands.  The two b x b block transfers of a step go
-// through the TMA engine instead of the load/store units, as one tensor copy each over a 3-D tensor map of the
-// skewed band storage (rows beyond the matrix are clipped by the hardware, so partial blocks need no special
-// path): the carried block is updated in place in shared memory and written back (shared -> global, bulk
-// group), the next block is fetched (global -> shared, mbarrier complete_tx).  The store overlaps the
-// diagonal-block products, the load overlaps the diagonal-block update.  The diagonal block itself stays in
-// registers; its Hermitian product needs a row and a column reduction.
+// Same algorithm and data flow as chase_kernel.  The b x b blocks are covered by a TR x TC thread grid with an
+// RB x CB sub-block per thread, so every offset is a compile-time constant off one per-thread base and the
+// products run on register operands.  The two b x b block transfers of a step go through the TMA engine instead
+// of the load/store units, as tensor copies over a 3-D tensor map of the skewed band storage (rows beyond the
+// matrix are clipped by the hardware, so partial blocks need no special path): the carried block is updated in
+// place in shared memory and written back (shared -> global, bulk group), the next block is fetched
+// (global -> shared, mbarrier complete_tx).  The diagonal block itself stays in registers; its Hermitian product
+// needs a row and a column reduction.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -480,327 +476,8 @@ __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;
 // shared-memory writes only (the block a tensor store is about to read): does not wait for global stores in flight
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int TB, int TR, int TC, int RB, int CB>
-__global__ void __launch_bounds__(CT, 1) chase_tma_kernel(ChaseArgs g, const __grid_constant__ CUtensorMap tmap) {
-  static_assert(TR * RB == TB && TC * CB == TB && TR * TC <= CT && TB <= CT, "exact cover");
-  constexpr int LDB = TB;        // dense box layout of the tensor copies
-  constexpr int LDP = TB + 1;    // partial sums: odd leading dimension, conflict-free in both directions
-  constexpr int LD = 2 * TB;
-  constexpr int NP = (TR > TC) ? TR : TC;
-  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
-  if (!g.mask.on(chain)) return;
-  extern __shared__ __align__(128) unsigned char smem_tma[];
-  const int n = g.n;
-  cplx* Bc = reinterpret_cast<cplx*>(smem_tma);      // [TB][LDB]
-  cplx* vs = Bc + LDB * TB;
-  cplx* vp = vs + TB;
-  cplx* us = vp + TB;
-  cplx* xs = us + TB;
-  cplx* tu = xs + TB;
-  cplx* wc = tu + TB;
-  cplx* part = wc + TB;                              // [NP][LDP]
-  cplx* red = part + NP * LDP;                       // [32]
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(red + 32);
-  const int tid = threadIdx.x;
-  const bool act = tid < TR * TC;
-  const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
-  const int soff = cj * LDB + ri;
-  const int goff = cj * (LD - 1) + ri;
-  cplx* AB = g.AB + (size_t)chain * n * LD;
-  cplx* V = g.V + (size_t)chain * n * n;
-  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
-  int* prog = g.prog + (size_t)chain * n;
-  const cplx zero = make_double2(0.0, 0.0);
-  if (tid == 0) mbar_init(bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  unsigned ephase = 0;                               // parity of the next-block barrier
-  bool store_pending = false;
-
-#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
-#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
-#else
-  constexpr bool prof = false;
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-#define PH(i) do { } while (0)
-#endif
-  for (int s = p; s < n - 1; s += g.P) {
-    int k = 0, r0 = s + 1;
-    cplx taup = zero;
-    int lcar = 0;                                    // rows of the carried block in flight / in Bc
-    while (true) {
-      const int ln = min(TB, n - r0);
-      if (prof) tlast = clock64();
-      // Sweep s-1 must be two steps ahead (or finished).  The only element of this step's blocks that sweep s-1
-      // touches later than that is the bottom-right corner of the carried block (the first entry of the column its
-      // step k+1 annihilates): it is re-read here, after the wait, instead of being trusted from the early fetch.
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = k + 2;
-          while (ld_acquire(prog + s - 1) < need) __nanosleep(32);
-        }
-        __syncthreads();
-      }
-      if (k > 0) {
-        // the carried block (issued at the end of the previous step) must have landed; u = Bn vp
-        mbar_wait(bar, ephase);
-        ephase ^= 1;
-        if (lcar == TB) {
-          if (tid == 0) Bc[(TB - 1) * LDB + TB - 1] = ldg2(AB + (size_t)(r0 - 1) * LD + TB);
-          __syncthreads();
-        }
-        if (act) {
-          cplx acc[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) acc[q] = zero;
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const cplx vj = vp[cj + cc * TC];
-#pragma unroll
-            for (int q = 0; q < RB; ++q)
-              if (ri + q * TR < lcar) cfma(acc[q], Bc[soff + cc * TC * LDB + q * TR], vj);
-          }
-#pragma unroll
-          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
-        }
-        __syncthreads();
-        for (int i = tid; i < lcar; i += CT) {
-          cplx u = part[i];
-#pragma unroll 5
-          for (int q = 1; q < TC; ++q) u = cadd(u, part[q * LDP + i]);
-          us[i] = u;
-          // the column to annihilate comes out of the same pass: x = Bc[:, 0] - taup u (vp[0] = 1)
-          const cplx t = cmul(taup, u);
-          tu[i] = t;
-          xs[i] = csub(Bc[i], t);
-        }
-      }
-      PH(0);
-      if (k > 0 && ln <= 1) {
-        __syncthreads();
-        for (int idx = tid; idx < ln * TB; idx += CT) {
-          const int i = idx % ln, j = idx / ln;
-          cplx a = Bc[j * LDB + i];
-          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
-          stg2(AB + (size_t)(r0 - TB + j) * LD + (TB + i - j), a);
-        }
-        for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
-        break;
-      }
-      PH(1);
-      // ---- prefetch the lower triangle of the diagonal block into registers
-      cplx* baseD = AB + (size_t)r0 * LD + goff;
-      cplx dreg[RB][CB];
-#pragma unroll
-      for (int c = 0; c < CB; ++c)
-#pragma unroll
-        for (int q = 0; q < RB; ++q) {
-          const int i = ri + q * TR, j = cj + c * TC;
-          if (q * TR + TR - 1 < c * TC) continue;      // sub-block wholly above the diagonal: never referenced
-          dreg[q][c] = (act && i >= j && i < ln) ? ldg2(baseD + c * TC * (LD - 1) + q * TR) : zero;
-        }
-      // ---- A. column to annihilate
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
-      }
-      __syncthreads();
-      // ---- B. reflector
-      cplx tau; double beta;
-      larfg_block(xs, vs, ln, red, tau, beta);
-      PH(2);
-      for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
-      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
-      cplx vr[RB];
-#pragma unroll
-      for (int q = 0; q < RB; ++q) vr[q] = (ri + q * TR < ln) ? vs[ri + q * TR] : zero;
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
-      } else {
-        // ---- C. carried block, updated in place, then written back by the bulk-copy engine
-        // (v^H tu rides along as column TB of the partial sums: LDP = TB + 1)
-        if (act) {
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            cplx acc = zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[soff + cc * TC * LDB + q * TR]);
-            part[ri * LDP + cj + cc * TC] = acc;
-          }
-          if (cj == 0) {
-            cplx acc = zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q)
-              if (ri + q * TR < ln) cfmac(acc, vr[q], tu[ri + q * TR]);
-            part[ri * LDP + TB] = acc;
-          }
-        }
-        __syncthreads();
-        PH(1);
-        const cplx ctau = cconj(tau);
-        for (int j = tid; j < TB; j += CT) {
-          cplx z = part[j], c = part[TB];
-#pragma unroll 5
-          for (int q = 1; q < TR; ++q) { z = cadd(z, part[q * LDP + j]); c = cadd(c, part[q * LDP + TB]); }
-          cfms(z, c, cconj(vp[j]));
-          wc[j] = cmul(ctau, z);
-        }
-        __syncthreads();
-        if (act) {
-          cplx tur[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) tur[q] = tu[min(ri + q * TR, TB - 1)];
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            const cplx cvp = cconj(vp[j]), wj = wc[j];
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              const int i = ri + q * TR;
-              if (i < ln) {
-                cplx o = Bc[soff + cc * TC * LDB + q * TR];
-                cfms(o, tur[q], cvp);
-                cfms(o, vr[q], wj);
-                if (j == 0) o = (i == 0) ? make_double2(beta, 0.0) : zero;
-                Bc[soff + cc * TC * LDB + q * TR] = o;
-              }
-            }
-          }
-        }
-        fence_async();                                // generic-proxy writes of Bc -> visible to the bulk engine
-        __syncthreads();
-        if (tid == 0) {
-          // one tensor copy: rows r0 .. r0+TB-1 (rows >= n are clipped), columns r0-TB .. r0-1 of this chain
-          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                       ::"l"(&tmap), "r"(2 * r0), "r"(r0 - TB), "r"(chain), "r"(smem_u32(Bc)) : "memory");
-          bulk_commit();
-        }
-        store_pending = true;
-      }
-      PH(3);
-      // ---- D. diagonal block from registers: x = tau D v, D Hermitian (lower part held)
-      {
-        // row part: sum_{j <= i} D[i,j] v[j]
-        if (act) {
-          cplx acc[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) acc[q] = zero;
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            const cplx vj = (j < ln) ? vs[j] : zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q) {
-              if (q * TR + TR - 1 < cc * TC) continue;
-              cplx a = dreg[q][cc];
-              if (ri + q * TR == j) a.y = 0.0;
-              cfma(acc[q], a, vj);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < RB; ++q) part[cj * LDP + ri + q * TR] = acc[q];
-        }
-        __syncthreads();
-        for (int i = tid; i < ln; i += CT) {
-          cplx wv = part[i];
-#pragma unroll 5
-          for (int q = 1; q < TC; ++q) wv = cadd(wv, part[q * LDP + i]);
-          xs[i] = wv;
-        }
-        __syncthreads();
-        // column part: sum_{i > j} conj(D[i,j]) v[i]
-        if (act) {
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            const int j = cj + cc * TC;
-            cplx acc = zero;
-#pragma unroll
-            for (int q = 0; q < RB; ++q)
-              if (q * TR + TR - 1 >= cc * TC && ri + q * TR > j) cfmac(acc, dreg[q][cc], vr[q]);
-            part[ri * LDP + j] = acc;
-          }
-        }
-        __syncthreads();
-        cplx dot = zero;
-        for (int i = tid; i < ln; i += CT) {
-          cplx wv = xs[i];
-#pragma unroll 5
-          for (int q = 0; q < TR; ++q) wv = cadd(wv, part[q * LDP + i]);
-          wv = cmul(tau, wv);
-          xs[i] = wv;
-          cfmac(dot, wv, vs[i]);
-        }
-        dot = block_sum(dot, red);
-        cplx alpha = cmul(tau, dot);
-        alpha.x *= -0.5; alpha.y *= -0.5;
-        for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
-        __syncthreads();
-      }
-      PH(4);
-      // ---- next block: fetch with the bulk engine while the diagonal block is updated and stored
-      const int r1 = r0 + ln;
-      const int l2 = (r1 < n) ? min(TB, n - r1) : 0;
-      if (store_pending) {
-        if (tid == 0) bulk_wait_read();               // the write-back has finished reading Bc
-        __syncthreads();
-      }
-      if (l2 > 0) {
-        if (tid == 0) {
-          fence_async();
-          mbar_expect_tx(bar, (unsigned)(TB * TB * sizeof(cplx)));   // the full box counts, clipped rows are zero-filled
-          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                       ::"r"(smem_u32(Bc)), "l"(&tmap), "r"(2 * r1), "r"(r0), "r"(chain), "r"(smem_u32(bar)) : "memory");
-        }
-      }
-      PH(5);
-      // ---- D update and store (lower part, from registers)
-      if (act) {
-        cplx wr[RB];
-#pragma unroll
-        for (int q = 0; q < RB; ++q) wr[q] = xs[min(ri + q * TR, TB - 1)];
-#pragma unroll
-        for (int cc = 0; cc < CB; ++cc) {
-          const int j = cj + cc * TC;
-          const cplx cwj = cconj(xs[j]), cvj = cconj(vs[j]);
-#pragma unroll
-          for (int q = 0; q < RB; ++q) {
-            const int i = ri + q * TR;
-            if (q * TR + TR - 1 >= cc * TC && i >= j && i < ln) {
-              cplx a = dreg[q][cc];
-              if (i == j) a.y = 0.0;
-              cfms(a, vr[q], cwj);
-              cfms(a, wr[q], cvj);
-              if (i == j) a.y = 0.0;
-              stg2(baseD + cc * TC * (LD - 1) + q * TR, a);
-            }
-          }
-        }
-      }
-      if (store_pending) {
-        if (tid == 0) bulk_wait_all();                // write-back performed in global memory
-        store_pending = false;
-      }
-      if (l2 == 0) break;
-      for (int i = tid; i < ln; i += CT) vp[i] = vs[i];
-      taup = tau;
-      lcar = l2;
-      __syncthreads();
-      PH(6);
-      if (tid == 0) { fence_async(); st_release(prog + s, k + 1); }
-      PH(7);
-      r0 = r1;
-      ++k;
-    }
-    __syncthreads();
-    if (tid == 0) { fence_async(); __threadfence(); st_release(prog + s, 1 << 30); }
-  }
-  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
-#undef PH
-}
-
 // ---- TMA chase kernel with a helper warp -------------------------------------------------------------------
-// Same arithmetic as chase_tma_kernel.  Everything that waits on the memory system -- the progress poll of the
+// Everything that waits on the memory system -- the progress poll of the
 // previous sweep, the tensor copies of the carried block (store, wait, fetch of the next block), the re-read of
 // the corner element, the fence + release that publishes a step -- is done by lane 0 of a 17th warp, so the 512
 // compute threads only ever wait on named barriers the helper has usually reached already:
@@ -1563,8 +1240,7 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
   DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
   const int cap = h->nsm * per_sm;
   if (cap < 1) { h->err = "dw_band_chase: kernel does not fit"; return DWHMC_E_CUDA; }
-  int P = std::max(1, std::min(4, cap / B));
-  if (const char* e = getenv("DWHMC_BAND_P")) P = std::max(1, std::min(atoi(e), cap));
+  const int P = std::max(1, std::min(4, cap / B));
   // ticket kernel: one launch over all chains with every CTA that fits (at most 4 per chain)
   const int per_launch = tickets ? B : std::max(1, cap / P);      // chains per launch
   std::lock_guard<std::mutex> lock(g_chase_mutex);
@@ -1577,18 +1253,19 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
     a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.prog = h->band_prog;
     a.n = n; a.b = bw; a.LD = h->band_LD; a.KT = h->band_KT; a.P = P; a.c0 = c0; a.mask = mask;
     a.next = h->band_prog + (size_t)n * B; a.B = B; a.stride = 1; a.status = h->status;
-    static const bool no_tail = getenv("DWHMC_BAND_NOTAIL") != nullptr;
-    const bool tail = tickets && !no_tail && n - 1 - bw >= 1;
+    const bool tail = tickets && n - 1 - bw >= 1;
     a.nsweep = tail ? n - 1 - bw : n - 1;
+#ifdef DWHMC_CHASE_PROF                                  // phase clocks of CTA 0 (experiments; needs the kernels built with the flag)
     static long long* clk_dev = nullptr;
-    static const bool want_clk = getenv("DWHMC_BAND_CLK") != nullptr;
-    if (want_clk && !clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
-    a.clk = (want_clk && c0 == 0) ? clk_dev : nullptr;
+    if (!clk_dev) cudaMalloc(&clk_dev, 8 * sizeof(long long));
+    a.clk = (c0 == 0) ? clk_dev : nullptr;
+#else
+    a.clk = nullptr;
+#endif
     const int nch = std::min(per_launch, B - c0);
     int nctas = nch * P;
     if (tickets) {
       nctas = std::min(cap, 4 * B);
-      if (const char* e = getenv("DWHMC_BAND_CTAS")) nctas = std::max(1, std::min(atoi(e), cap));
       auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
       a.stride = std::max(1, nctas - 2 * B);                     // spare CTAs visit every chain in turn
       while (gcd(a.stride, B) != 1) ++a.stride;
@@ -1617,30 +1294,26 @@ static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthread
   return DWHMC_OK;
 }
 
-template <bool HELPER, int TB, int TR, int TC, int RB, int CB>
+template <int TB, int TR, int TC, int RB, int CB>
 static int chase_tma_dispatch(Handle* h, Mask mask) {
-  const int nthreads = HELPER ? chase_nc(TR, TC) + 32 : CT;
+  const int nthreads = chase_nc(TR, TC) + 32;
   const size_t smem = chase_tma_smem<TB, TR, TC>();
-  const void* kern = nullptr;
-  if constexpr (HELPER) kern = (const void*)chase_tmah_kernel<TB, TR, TC, RB, CB>;
-  else kern = (const void*)chase_tma_kernel<TB, TR, TC, RB, CB>;
+  const void* kern = (const void*)chase_tmah_kernel<TB, TR, TC, RB, CB>;
   static bool attr[64] = {false};
   if (!attr[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[h->device & 63] = true;
   }
-  static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap), "tensor map storage");
+  static_assert(sizeof(CUtensorMap) <= sizeof(h->band_tmap_a), "tensor map storage");
   if (!h->band_tmap_set) {
-    constexpr int pcc = chase_pcc(CB), npiece = (CB + pcc - 1) / pcc, pw = pcc * TC;   // column pieces of the helper-warp kernel
-    DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap), TB));
+    constexpr int pcc = chase_pcc(CB), npiece = (CB + pcc - 1) / pcc, pw = pcc * TC;   // column pieces of the carried block
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_a), std::min(pw, TB)));
     DW_TRY(make_band_tensor_map(h, reinterpret_cast<CUtensorMap*>(h->band_tmap_b), TB - pw * (npiece - 1)));
     h->band_tmap_set = true;
   }
-  return chase_launch_loop(h, mask, kern, nthreads, smem, HELPER, [&](ChaseArgs& a, int ctas) -> int {
-    void* targs_h[] = {&a, h->band_tmap_a, h->band_tmap_b};
-    void* targs[] = {&a, h->band_tmap};
-    DW_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(nthreads), HELPER ? targs_h : targs, smem, h->stream));
+  return chase_launch_loop(h, mask, kern, nthreads, smem, true, [&](ChaseArgs& a, int ctas) -> int {
+    void* targs[] = {&a, h->band_tmap_a, h->band_tmap_b};
+    DW_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(nthreads), targs, smem, h->stream));
     return DWHMC_OK;
   });
 }
@@ -1654,28 +1327,18 @@ int dw_band_chase(Handle* h, Mask mask) {
   const int n = h->n, B = h->B, bw = h->band_b;
   DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * ((size_t)n + 1) * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
+  // DWHMC_BAND_GENERIC=1: the generic chase kernel (any half-bandwidth <= 101, load/store units instead of TMA) -- the
+  // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
-  // DWHMC_BAND_HELPER=0: the variant without the helper warp (every thread waits on the memory system in turn).
-  // With the helper warp the compute threads fill at most 15 warps (16 warps x 128 registers is the register file).
-  static const bool helper = getenv("DWHMC_BAND_HELPER") ? atoi(getenv("DWHMC_BAND_HELPER")) != 0 : true;
-  if (!generic && helper && bw == 100) DW_TRY((chase_tma_dispatch<true, 100, 25, 19, 4, 6>(h, mask)));
-  else if (!generic && helper && bw == 84) DW_TRY((chase_tma_dispatch<true, 84, 21, 21, 4, 4>(h, mask)));
-  else if (!generic && helper && bw == 76) DW_TRY((chase_tma_dispatch<true, 76, 19, 19, 4, 4>(h, mask)));
-  else if (!generic && helper && bw == 68) DW_TRY((chase_tma_dispatch<true, 68, 17, 17, 4, 4>(h, mask)));
-  else if (!generic && helper && bw == 60) DW_TRY((chase_tma_dispatch<true, 60, 15, 20, 4, 3>(h, mask)));
-  else if (!generic && helper && bw == 52) DW_TRY((chase_tma_dispatch<true, 52, 13, 26, 4, 2>(h, mask)));
-  else if (!generic && helper && bw == 44) DW_TRY((chase_tma_dispatch<true, 44, 22, 11, 2, 4>(h, mask)));
-  else if (!generic && helper && bw == 36) DW_TRY((chase_tma_dispatch<true, 36, 18, 18, 2, 2>(h, mask)));
-  else if (!generic && helper && bw == 28) DW_TRY((chase_tma_dispatch<true, 28, 14, 14, 2, 2>(h, mask)));
-  else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<false, 100, 25, 20, 4, 5>(h, mask)));
-  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<false, 84, 21, 21, 4, 4>(h, mask)));
-  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<false, 76, 19, 19, 4, 4>(h, mask)));
-  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<false, 68, 17, 17, 4, 4>(h, mask)));
-  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<false, 60, 15, 20, 4, 3>(h, mask)));
-  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<false, 52, 13, 26, 4, 2>(h, mask)));
-  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<false, 44, 22, 22, 2, 2>(h, mask)));
-  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<false, 36, 18, 18, 2, 2>(h, mask)));
-  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<false, 28, 14, 14, 2, 2>(h, mask)));
+  if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
+  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
+  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
+  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));
+  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<60, 15, 20, 4, 3>(h, mask)));
+  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<52, 13, 26, 4, 2>(h, mask)));
+  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<44, 22, 11, 2, 4>(h, mask)));
+  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<36, 18, 18, 2, 2>(h, mask)));
+  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<28, 14, 14, 2, 2>(h, mask)));
   else {
     const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
     static bool attr_set[64] = {false};

@@ -171,9 +171,6 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ double dneg(double x) {      // sign flip on the integer pipe
-  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
-}
 __device__ __forceinline__ cplx ldcg(const cplx* p) {   // L2 only: Z is shared between CTAs across wavefronts
   cplx v;
   asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -425,8 +422,6 @@ void dw_band_apply_items(Handle* h, std::vector<int>& items4) {
   const int nwave = (int)h->band_wave_start.size() - 1;
   const int nstrip = (n - (h->N / 16) * 16 + 7) / 8;
   const int maxparts = std::max(1, (nstrip + A2_WARPS - 1) / A2_WARPS);
-  int force = 0;
-  if (const char* e = getenv("DWHMC_APPLY_PARTS")) force = atoi(e);
   items4.clear();
   int prev = 0;
   for (int t = 0; t < nwave; ++t) {
@@ -434,7 +429,6 @@ void dw_band_apply_items(Handle* h, std::vector<int>& items4) {
     const int nsub = w1 - w0;
     if (nsub <= 0) continue;
     int np = (13 * h->nsm + 10 * nsub * h->B - 1) / (10 * nsub * h->B);
-    if (force > 0) np = force;
     np = std::max(1, std::min(np, maxparts));
     for (int c = 0; c < h->B; ++c)
       for (int i = w0; i < w1; ++i)

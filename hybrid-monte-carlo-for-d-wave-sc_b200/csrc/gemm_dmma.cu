@@ -250,12 +250,7 @@ int launch(Handle* h, const ZgemmArgs& a) {
   g.skip_flag = a.skip_flag; g.skip_cols = a.skip_cols; g.stairA = a.stairA;
   g.ksplit = a.ksplit > 1 ? a.ksplit : 1; g.sCk = a.sCk;
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch * g.ksplit);
-  static int pad = -1;                  // DWHMC_GEMM_PAD=KB: extra dynamic smem (experiment: limit CTAs/SM)
-  if (pad < 0) {
-    const char* e = getenv("DWHMC_GEMM_PAD"); pad = e ? atoi(e) * 1024 : 0;
-    if (pad) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM + pad);
-  }
-  kern<<<grid, NTHREADS, T::SMEM + pad, a.stream ? a.stream : h->stream>>>(g);
+  kern<<<grid, NTHREADS, T::SMEM, a.stream ? a.stream : h->stream>>>(g);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
 }
@@ -266,18 +261,13 @@ int dw_zgemm(Handle* h, const ZgemmArgs& a) {
   if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return DWHMC_OK;
   if (a.K <= 0 && a.beta == 1.0) return DWHMC_OK;
   const bool small_m = a.M <= 32;
-  static int big = -1;                  // DWHMC_GEMM_BIG=1: 128x64 tiles for the tall updates (experiment)
-  if (big < 0) { const char* e = getenv("DWHMC_GEMM_BIG"); big = e ? atoi(e) : 0; }
-  const bool tall = big && a.M >= 256;
   if (a.opA == 0 && a.opB == 1) {
-    if (tall) return launch<128, 64, 4, 2, 0, 1>(h, a);
     return launch<64, 64, 2, 4, 0, 1>(h, a);
   } else if (a.opA == 1 && a.opB == 0) {
     if (small_m) return launch<32, 128, 1, 8, 1, 0>(h, a);
     return launch<64, 64, 2, 4, 1, 0>(h, a);
   } else if (a.opA == 0 && a.opB == 0) {
     if (small_m) return launch<32, 128, 1, 8, 0, 0>(h, a);
-    if (tall) return launch<128, 64, 4, 2, 0, 0>(h, a);
     return launch<64, 64, 2, 4, 0, 0>(h, a);
   }
   h->err = "dw_zgemm: unsupported op combination";

@@ -328,86 +328,8 @@ __global__ void __cluster_dims__(CC, 1, 1) __launch_bounds__(CT) colstep_kernel(
 // (row pass) / slot I (column pass) of ypart, so every row of block X receives exactly one
 // contribution in each slot 0..nt-1 and the reduction in colstep_kernel has a fixed order.
 constexpr int TS = 64;
-constexpr int TLD = TS + 1;   // padded: the column pass reads with stride TLD, conflict-free
-constexpr size_t HEMV_SMEM = sizeof(cplx) * (TS * TLD + 2 * TS + 8 * TS);
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred, unsigned long long pol) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(sa), "l"(gmem), "r"(sz),
-               "l"(pol));
-}
-
-__global__ void __launch_bounds__(256) hemv_lower_kernel(const cplx* __restrict__ Aall, const cplx* __restrict__ Vall,
-                                                         cplx* __restrict__ ypart, int n, int B, int b0, int j,
-                                                         Mask mask) {
-  const int b = b0 + blockIdx.y;
-  if (!mask.on(b)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* As = reinterpret_cast<cplx*>(smem_raw);   // [TS][TLD], column-major tile
-  cplx* vr = As + TS * TLD;                       // v on the tile's rows
-  cplx* vc = vr + TS;                             // v on the tile's columns
-  cplx* red = vc + TS;                            // [2][4][TS]
-  const int q0 = j + 1, m = n - q0;
-  // tile (I, J), I >= J, from the linear index t = I (I + 1) / 2 + J
-  const int t = blockIdx.x;
-  int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((I + 1) * (I + 2) / 2 <= t) ++I;
-  while (I * (I + 1) / 2 > t) --I;
-  const int J = t - I * (I + 1) / 2;
-  const int R0 = I * TS, C0 = J * TS;
-  const int tid = threadIdx.x;
-  const size_t mat = (size_t)b * n * n;
-  const cplx* A = Aall + mat + (size_t)(q0 + C0) * n + q0 + R0;
-  const cplx* v = Vall + mat + (size_t)j * n + q0;
-  const unsigned long long pol = policy_evict_first();
-#pragma unroll
-  for (int it = 0; it < (TS * TS) / 256; ++it) {
-    const int idx = tid + it * 256;
-    const int r = idx & (TS - 1), c = idx >> 6;
-    const bool p = (R0 + r < m) && (C0 + c < m);
-    cp_async16(As + c * TLD + r, p ? A + (size_t)c * n + r : A, p, pol);
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-  if (tid < TS) vr[tid] = (R0 + tid < m) ? v[R0 + tid] : make_double2(0.0, 0.0);
-  else if (tid < 2 * TS) vc[tid - TS] = (C0 + tid - TS < m) ? v[C0 + tid - TS] : make_double2(0.0, 0.0);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
-  const int x = tid & (TS - 1), q = tid >> 6;     // x: row (row pass) / column (column pass); q: 16-wide group
-  const bool diag = (I == J);
-  cplx acc = make_double2(0.0, 0.0), acc2 = make_double2(0.0, 0.0);
-#pragma unroll 4
-  for (int cc = 0; cc < 16; ++cc) {
-    const int c = q * 16 + cc;
-    if (!diag || c <= x) cfma(acc, As[c * TLD + x], vc[c]);
-  }
-#pragma unroll 4
-  for (int rr = 0; rr < 16; ++rr) {
-    const int r = q * 16 + rr;
-    if (!diag || r > x) cfmac(acc2, As[x * TLD + r], vr[r]);
-  }
-  red[q * TS + x] = acc;
-  red[(4 + q) * TS + x] = acc2;
-  __syncthreads();
-  if (tid < 2 * TS) {
-    const int which = tid >> 6, xx = tid & (TS - 1);
-    const cplx* rp = red + which * 4 * TS + xx;
-    cplx sum = cadd(cadd(rp[0], rp[TS]), cadd(rp[2 * TS], rp[3 * TS]));
-    if (diag) {
-      if (which == 0) {
-        const cplx* rq = red + 4 * TS + xx;
-        sum = cadd(sum, cadd(cadd(rq[0], rq[TS]), cadd(rq[2 * TS], rq[3 * TS])));
-        if (R0 + xx < m) ypart[((size_t)I * B + b) * n + q0 + R0 + xx] = sum;
-      }
-    } else if (which == 0) {
-      if (R0 + xx < m) ypart[((size_t)J * B + b) * n + q0 + R0 + xx] = sum;
-    } else {
-      if (C0 + xx < m) ypart[((size_t)I * B + b) * n + q0 + C0 + xx] = sum;
-    }
-  }
-}
-
-// Register-path variant of hemv_lower_kernel (same tiles, same ypart slots, same result layout):
+// Register path (the shared-memory staged and the persistent warp-ring variants of round 1 measured slower and were
+// removed in round 2; same tiles, same ypart slots, same result layout):
 // no shared-memory staging.  Warp w of the CTA owns columns 8w..8w+7 of the 64x64 tile, lane l the
 // rows l and l+32; the 16 elements of a lane are loaded straight into registers (16 independent
 // 16-byte requests per thread, each warp request one contiguous 512-byte segment) and used for both
@@ -564,179 +486,6 @@ __global__ void __launch_bounds__(256, 2) hemv_reg_kernel(const cplx* __restrict
   }
 }
 
-// Persistent, warp-autonomous variant (hemv_variant 2).  Every warp is an independent worker with its
-// own list of (tile, chain) items and its own cp.async ring in shared memory: a stage is one 64 x 8
-// sub-tile (8 KB) plus the 8 entries of v on its columns; each lane copies exactly the 16 elements it
-// will consume (rows l, l+32 of the 8 columns), so a stage needs no block barrier, and loads stay in
-// flight across tile boundaries.  A warp walks the 8 sub-tiles of a tile, keeps the row sums in
-// registers, reduces the column sums with the transposing butterfly, and writes the tile's results
-// alone.  One CTA per SM; its shared memory is sized to leave room for the column-step CTAs of the
-// other chain group.
-constexpr int HW_WARPS = 7;
-constexpr int HW_DEPTH = 3;
-constexpr int HW_STAGE = 64 * 8 + 8;                           // cplx per stage: sub-tile + v on its columns
-constexpr int HW_PER_WARP = HW_DEPTH * HW_STAGE + 2 * 64 + 64;  // + v on the rows (2 items) + column sums
-constexpr size_t HW_SMEM = sizeof(cplx) * HW_WARPS * HW_PER_WARP;
-
-__device__ __forceinline__ void cp_async16_plain(void* smem, const void* gmem, bool pred) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
-}
-
-__device__ __forceinline__ void tile_decode(int t, int& I, int& J) {
-  I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((I + 1) * (I + 2) / 2 <= t) ++I;
-  while (I * (I + 1) / 2 > t) --I;
-  J = t - I * (I + 1) / 2;
-}
-
-__global__ void __launch_bounds__(HW_WARPS * 32, 1) hemv_warp_kernel(const cplx* __restrict__ Aall,
-                                                                     const cplx* __restrict__ Vall,
-                                                                     cplx* __restrict__ ypart, int n, int B, int b0,
-                                                                     int nb, int j, int ntiles, Mask mask) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cplx* ring = reinterpret_cast<cplx*>(smem_raw) + (size_t)warp * HW_PER_WARP;
-  cplx* vrb = ring + HW_DEPTH * HW_STAGE;       // [2][64]
-  cplx* cs = vrb + 2 * 64;                      // [64]
-  const int q0 = j + 1, m = n - q0;
-  const int gw = blockIdx.x * HW_WARPS + warp, GW = gridDim.x * HW_WARPS;
-  const int nitems = ntiles * nb;
-  const cplx zero = make_double2(0.0, 0.0);
-
-  // issue cursor
-  int it_i = gw, sub_i = 0, I_i = 0, J_i = 0, b_i = 0, cnt_i = 0;
-  bool on_i = false;
-  auto setup_issue = [&]() {
-    while (it_i < nitems) {
-      b_i = b0 + it_i / ntiles;
-      if (mask.on(b_i)) { tile_decode(it_i % ntiles, I_i, J_i); on_i = true; return; }
-      it_i += GW;
-    }
-    on_i = false;
-  };
-  auto issue = [&](int stage) {
-    if (on_i) {
-      const int R0 = I_i * TS, C0 = J_i * TS, cl0 = sub_i * 8;
-      const bool diag = (I_i == J_i);
-      const size_t mat = (size_t)b_i * n * n;
-      const cplx* A = Aall + mat + (size_t)(q0 + C0 + cl0) * n + q0 + R0;
-      const cplx* v = Vall + mat + (size_t)j * n + q0;
-      cplx* st = ring + stage * HW_STAGE;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int rl = lane + 32 * hh, cl = cl0 + c;
-          const bool p = (R0 + rl < m) && (C0 + cl < m) && (!diag || rl >= cl);
-          cp_async16_plain(st + c * 64 + rl, p ? A + (size_t)c * n + rl : A, p);
-        }
-      if (lane < 8) {
-        const bool p = C0 + cl0 + lane < m;
-        cp_async16_plain(st + 512 + lane, p ? v + C0 + cl0 + lane : v, p);
-      }
-      if (sub_i == 0) {
-        cplx* vb = vrb + (cnt_i & 1) * 64;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int rl = lane + 32 * hh;
-          const bool p = R0 + rl < m;
-          cp_async16_plain(vb + rl, p ? v + R0 + rl : v, p);
-        }
-      }
-      if (++sub_i == 8) { sub_i = 0; ++cnt_i; it_i += GW; setup_issue(); }
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
-
-  setup_issue();
-#pragma unroll
-  for (int s = 0; s < HW_DEPTH - 1; ++s) issue(s);
-
-  // consume cursor
-  int it_c = gw, cnt_c = 0, stage = 0;
-  while (it_c < nitems) {
-    const int b = b0 + it_c / ntiles;
-    if (!mask.on(b)) { it_c += GW; continue; }
-    int I, J;
-    tile_decode(it_c % ntiles, I, J);
-    const int R0 = I * TS, C0 = J * TS;
-    const bool diag = (I == J);
-    cplx accR[2] = {zero, zero};
-    const cplx* vb = vrb + (cnt_c & 1) * 64;
-    for (int sub = 0; sub < 8; ++sub) {
-      issue((stage + HW_DEPTH - 1) % HW_DEPTH);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(HW_DEPTH - 1));
-      __syncwarp();
-      const cplx* st = ring + stage * HW_STAGE;
-      const cplx vr0 = vb[lane], vr1 = vb[lane + 32];
-      const int cl0 = sub * 8;
-      cplx accC[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const cplx vc = st[512 + c];
-        const cplx x0 = st[c * 64 + lane], x1 = st[c * 64 + lane + 32];
-        cfma(accR[0], x0, vc);
-        cfma(accR[1], x1, vc);
-        cplx sacc = zero;
-        if (!(diag && lane == cl0 + c)) cfmac(sacc, x0, vr0);
-        if (!(diag && lane + 32 == cl0 + c)) cfmac(sacc, x1, vr1);
-        accC[c] = sacc;
-      }
-      cplx r4[4], r2[2], r1;
-      {
-        const bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const cplx send = up ? accC[k] : accC[k + 4];
-          const cplx keep = up ? accC[k + 4] : accC[k];
-          r4[k] = cadd(keep, shfl_xor_c(send, 16));
-        }
-      }
-      {
-        const bool up = (lane & 8) != 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const cplx send = up ? r4[k] : r4[k + 2];
-          const cplx keep = up ? r4[k + 2] : r4[k];
-          r2[k] = cadd(keep, shfl_xor_c(send, 8));
-        }
-      }
-      {
-        const bool up = (lane & 4) != 0;
-        const cplx send = up ? r2[0] : r2[1];
-        const cplx keep = up ? r2[1] : r2[0];
-        r1 = cadd(keep, shfl_xor_c(send, 4));
-      }
-      r1 = cadd(r1, shfl_xor_c(r1, 2));
-      r1 = cadd(r1, shfl_xor_c(r1, 1));
-      if ((lane & 3) == 0) cs[cl0 + (lane >> 2)] = r1;
-      __syncwarp();
-      stage = (stage + 1) % HW_DEPTH;
-    }
-    // results of the tile
-    if (diag) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int x = lane + 32 * hh;
-        if (R0 + x < m) ypart[((size_t)I * B + b) * n + q0 + R0 + x] = cadd(accR[hh], cs[x]);
-      }
-    } else {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int x = lane + 32 * hh;
-        if (R0 + x < m) ypart[((size_t)J * B + b) * n + q0 + R0 + x] = accR[hh];
-        if (C0 + x < m) ypart[((size_t)I * B + b) * n + q0 + C0 + x] = cs[x];
-      }
-    }
-    __syncwarp();
-    ++cnt_c;
-    it_c += GW;
-  }
-  asm volatile("cp.async.wait_group 0;\n" ::);
-}
-
 __global__ void lastd_kernel(const cplx* __restrict__ A, double* __restrict__ d, int n, int B, Mask mask) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B || !mask.on(b)) return;
@@ -756,8 +505,6 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
   static bool attr_set[64] = {false};
   if (!attr_set[h->device & 63]) {
     DW_CUDA(h, cudaFuncSetAttribute(colstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DW_CUDA(h, cudaFuncSetAttribute(hemv_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEMV_SMEM));
-    DW_CUDA(h, cudaFuncSetAttribute(hemv_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HW_SMEM));
     attr_set[h->device & 63] = true;
   }
   if (col_smem > 200 * 1024) { h->err = "dw_hetrd: matrix too large for the column-step kernel"; return DWHMC_E_BADARG; }
@@ -788,9 +535,6 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
   auto col_done = [&](int g) {
     if (G > 1) { cudaEventRecord(h->ev_col[g], hp[g]); cudaStreamWaitEvent(lp[g], h->ev_col[g], 0); }
   };
-  static const bool skip_hemv = getenv("DWHMC_SKIP_HEMV") != nullptr;   // timing experiments only (results invalid)
-  static const bool skip_col = getenv("DWHMC_SKIP_COL") != nullptr;
-  static const bool skip_her2k = getenv("DWHMC_SKIP_HER2K") != nullptr;
   ColArgs ca;
   ca.A = h->A; ca.V = h->V; ca.W = W; ca.ypart = h->ypart; ca.P1 = h->P1; ca.P2 = h->P2; ca.tau = h->tau;
   ca.d = h->d; ca.e = h->e; ca.n = n; ca.B = B; ca.mask = mask;
@@ -803,23 +547,13 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       const int nt = (m + TS - 1) / TS;
       for (int g = 0; g < G; ++g) {
         ca.j = j; ca.finish_prev = (i > 0); ca.make_ref = 1; ca.b0 = gb0[g];
-        static const bool dots_in_hemv = getenv("DWHMC_DOTS_IN_HEMV") != nullptr;   // experiment: no gain measured
-        ca.skip_dots = (h->hemv_variant == 1 && dots_in_hemv) ? 1 : 0;
-        if (!skip_col) colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
+        ca.skip_dots = 0;
+        colstep_kernel<<<gB[g] * CC, CT, col_smem, hp[g]>>>(ca);
         DW_LAUNCH_CHECK(h);
         col_done(g);
         dim3 grid(nt * (nt + 1) / 2, gB[g]);
-        if (skip_hemv) { bulk_done(g); continue; }
         if (h->profiling >= 2) cudaEventRecord(h->ev_begin, lp[g]);
-        if (h->hemv_variant == 2) {
-          const int items = (int)grid.x * gB[g];
-          const int ctas = std::min(h->nsm, (items + HW_WARPS - 1) / HW_WARPS);
-          hemv_warp_kernel<<<ctas, HW_WARPS * 32, HW_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], gB[g], j, (int)grid.x, mask);
-        } else if (h->hemv_variant == 0) hemv_lower_kernel<<<grid, 256, HEMV_SMEM, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask);
-        else {
-          dim3 grid2(grid.x + (ca.skip_dots ? CC : 0), gB[g]);
-          hemv_reg_kernel<<<grid2, 256, 0, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask, W, h->P1, h->P2, j0, (int)grid.x);
-        }
+        hemv_reg_kernel<<<grid, 256, 0, lp[g]>>>(h->A, h->V, h->ypart, n, B, gb0[g], j, mask, W, h->P1, h->P2, j0, (int)grid.x);
         DW_LAUNCH_CHECK(h);
         if (h->profiling >= 2) {
           cudaEventRecord(h->ev_end, lp[g]);
@@ -847,7 +581,7 @@ int dw_hetrd(Handle* h, cplx* W, Mask mask) {
       a.C = h->A + (size_t)j1 * n + j1;
       a.alpha = -1.0; a.beta = 1.0; a.opA = 0; a.opB = 1; a.lower = 1; a.batch = gB[g]; a.mask = mask;
       a.b0 = gb0[g]; a.stream = lp[g];
-      if (!skip_her2k) DW_TRY(dw_zgemm(h, a));
+      DW_TRY(dw_zgemm(h, a));
       bulk_done(g);
     }
   }

@@ -139,8 +139,7 @@ struct Handle {
   int* band_items_dev = nullptr;          // device [4*band_nitems]
   int* band_sync = nullptr;               // device [1 + B*nwave]: ticket, published items per (chain, wavefront)
   int* band_blk_s0_dev = nullptr; int* band_blk_k_dev = nullptr;
-  alignas(64) unsigned char band_tmap[128] = {};   // CUtensorMap of the band storage (TMA chase kernel)
-  alignas(64) unsigned char band_tmap_a[128] = {};  // the same view with narrower boxes: column pieces of the carried block
+  alignas(64) unsigned char band_tmap_a[128] = {};  // CUtensorMaps of the band storage (TMA chase kernel): column pieces of the carried block
   alignas(64) unsigned char band_tmap_b[128] = {};
   bool band_tmap_set = false;
   // transport / spectra workspace (transport.cu), allocated on first use
@@ -150,7 +149,6 @@ struct Handle {
   // particle-hole symmetry of the BdG matrix (tau_y H^* tau_y = -H): only the N eigenvectors of the
   // upper half of the spectrum are back-transformed, the rest are their conjugate partners
   int nsm = 148;                // SMs of the device
-  int hemv_variant = 1;         // 1: register-path hemv (default); 0: shared-memory staged (env DWHMC_HEMV)
   int ph_mode = 1;              // env DWHMC_PH=0 switches the shortcut off
   int* halfflag = nullptr;      // device [B]: 1 = this chain's last eigensolve used the shortcut
   long long launches = 0;

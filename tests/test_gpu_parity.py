@@ -721,15 +721,13 @@ def test_two_handles_concurrently(dw):
         cbs[i].close()
 
 
-@pytest.mark.parametrize("hemv", ["1", "0", "2"])
-def test_dense_route_and_hemv_variants(dw, monkeypatch, hemv):
+def test_dense_route_against_oracle(dw, monkeypatch):
     """The dense eigensolver route (DWHMC_BAND=0: blocked tridiagonalisation + back-transformation; the route of
-    lattices without a compile-time chase kernel, e.g. L = 32) with each trailing-matrix-product kernel
-    (DWHMC_HEMV: 1 register path, 0 shared-memory staged, 2 persistent warp rings) against the oracle."""
+    lattices whose half-bandwidth exceeds 100, e.g. L = 32, see tests/test_gpu_round2.py for that size) against the
+    oracle."""
     monkeypatch.setenv("DWHMC_BAND", "0")
-    monkeypatch.setenv("DWHMC_HEMV", hemv)
     cb, ps, sts, cs = make_batch(dw, 12, [3.0, 30.0, 300.0], 0.05, 2100)
-    monkeypatch.delenv("DWHMC_BAND"); monkeypatch.delenv("DWHMC_HEMV")
+    monkeypatch.delenv("DWHMC_BAND")
     assert cb.band_halfwidth() == 0
     n = 2 * 144
     E, U = cb.get_eigenvalues(), cb.get_eigenvectors()
@@ -754,12 +752,11 @@ def test_default_route_is_band_where_a_chase_kernel_exists(dw):
         cb.close()
 
 
-@pytest.mark.parametrize("switch", ["DWHMC_BAND_HELPER=0", "DWHMC_BAND_NOTAIL=1", "DWHMC_BAND_GENERIC=1"])
+@pytest.mark.parametrize("switch", ["DWHMC_BAND_GENERIC=1"])
 def test_chase_fallback_kernels(switch):
-    """The bulge-chase variants behind the (process-wide, read-once) switches -- the TMA kernel without helper warp and
-    with static sweep assignment, the helper kernel without the dense tail kernel, the generic LSU kernel -- against
-    LAPACK, each in a process of its own: eigenvalues, residual and unitarity of two chains at L = 8 (b = 36) and of a
-    rectangular lattice whose half-bandwidth is rounded up (5 x 13: 24 -> 28)."""
+    """The one fallback of the band route behind its (process-wide, read-once) switch -- the generic bulge-chase
+    kernel on the load/store units -- against LAPACK, in a process of its own: eigenvalues, residual and unitarity of
+    chains at L = 8 (b = 36) and of a rectangular lattice whose half-bandwidth is rounded up (5 x 13: 24 -> 28)."""
     import re
     import subprocess
     import sys
