@@ -641,7 +641,7 @@ int dwhmc_debug_stedc(dwhmc_handle hh, const double* d, const double* e, double*
   DW_TRY(h2d(h, h->d, d, sizeof(double) * (size_t)n * B));
   DW_TRY(h2d(h, h->e, tmp.data(), sizeof(double) * (size_t)n * B));
   DW_TRY(dw_stedc(h, no_mask()));
-  DW_TRY(dw_stedc_output(h, h->E_prop, h->U_prop, no_mask(), false));
+  DW_TRY(dw_stedc_output(h, h->E_prop, h->U_prop, no_mask(), false, 0));
   DW_TRY(d2h(h, w, h->E_prop, sizeof(double) * (size_t)n * B));
   std::vector<double> zc((size_t)2 * n * n * B);
   DW_TRY(d2h(h, zc.data(), h->U_prop, sizeof(cplx) * (size_t)n * n * B));

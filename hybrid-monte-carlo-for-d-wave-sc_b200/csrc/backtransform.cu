@@ -181,9 +181,12 @@ int dw_eigensolve(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
   }
   toc(1);
   tic();
-  DW_TRY(dw_stedc(h, mask));
+  // first eigenvector column (by rank) a chain flagged for the particle-hole shortcut needs: the back-transformation
+  // of the band route works on strips of 8 columns from (N / 16) * 16, the dense route's GEMM tiles are up to 128 wide
+  const int c_lo = (ph && h->ph_mode) ? (band ? (h->N / 16) * 16 : (h->N / 128) * 128) : 0;
+  DW_TRY(dw_stedc(h, mask, ph, c_lo));
   // band route: the tridiagonal eigenvectors go to h->A (the band is dead by now), in band row order
-  DW_TRY(dw_stedc_output(h, E_out, band ? h->A : U_out, mask, ph));
+  DW_TRY(dw_stedc_output(h, E_out, band ? h->A : U_out, mask, ph, c_lo));
   toc(2);
   tic();
   if (band) {

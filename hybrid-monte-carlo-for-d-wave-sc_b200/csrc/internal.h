@@ -192,8 +192,9 @@ int dw_hetrd(Handle* h, cplx* Wscratch, Mask mask);
 // stedc.cu: h->d, h->e -> eigenvalues E_out (ascending) and real eigenvectors written as complex into U_out.
 // ph: decide per chain (h->halfflag) whether the particle-hole shortcut applies; flagged chains only get
 // the columns of the upper half of the spectrum.
-int dw_stedc(Handle* h, Mask mask);
-int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph);
+// c_lo: first eigenvector column (rank) flagged chains need (0: all)
+int dw_stedc(Handle* h, Mask mask, bool ph = false, int c_lo = 0);
+int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph, int c_lo);
 // backtransform.cu: U <- Q U (flagged chains: upper-half columns only, then the partner columns)
 int dw_backtransform(Handle* h, cplx* U, Mask mask, bool ph);
 int dw_ph_mirror(Handle* h, double* E, cplx* U, Mask mask);

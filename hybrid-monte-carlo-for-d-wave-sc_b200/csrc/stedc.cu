@@ -363,6 +363,10 @@ constexpr size_t G_SMEM = sizeof(double) * GST * G_STAGE;
 struct GemmArgs {
   LevelArgs lv;
   int ntiles_n;   // column tiles per merge
+  // last level only: chains flagged for the particle-hole shortcut need the eigenvectors of rank >= c_lo only.
+  // Root j of the secular equation has rank <= j + (deflated values), so column tiles wholly below are skipped.
+  const int* halfflag;
+  int c_lo;
 };
 
 __global__ void __launch_bounds__(256) dc_gemm2_kernel(GemmArgs ga) {
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(256) dc_gemm2_kernel(GemmArgs ga) {
   const int k = g.kcnt[vo];
   const int m0 = blockIdx.x * GBM, n0 = tn * GBN;
   if (m0 >= m || n0 >= k) return;
+  if (ga.c_lo > 0 && ga.halfflag[b] != 0 && n0 + GBN - 1 + (m - k) < ga.c_lo) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -486,6 +491,34 @@ __global__ void __launch_bounds__(256) dc_finish_kernel(LevelArgs g) {
   }
 }
 
+// Last level, after the secular equation: all eigenvalues of the chain are known (unsorted).  The particle-hole
+// decision of dc_evals_kernel, made early so that the eigenvector GEMM of the last level can skip the columns of
+// the lower half of the spectrum: flag = (the level of rank n/2 + 1 is resolved from zero).
+__global__ void __launch_bounds__(256) dc_halfflag_kernel(const double* __restrict__ dnew, int* __restrict__ halfflag, int n,
+                                                          int ph, Mask mask) {
+  const int b = blockIdx.x;
+  if (!mask.on(b)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sd = reinterpret_cast<double*>(smem_raw);
+  __shared__ double red[32];
+  __shared__ double s_val;
+  double emax = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = dnew[(size_t)b * n + i];
+    sd[i] = v;
+    emax = fmax(emax, fabs(v));
+  }
+  emax = block_max(emax, red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = sd[i];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) rank += (sd[q] < v) || (sd[q] == v && q < i);
+    if (rank == n / 2 + 1) s_val = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) halfflag[b] = (ph && n >= 8 && s_val > 1e-4 * emax) ? 1 : 0;
+}
+
 // eigenvalues ascending; decide whether the particle-hole shortcut is safe for this chain: the
 // partner construction needs the second-smallest level of the upper half to be resolved from zero
 // (a pair (E, -E) alone is always fine, <psi, C psi> = 0 exactly; two pairs closer to zero than the
@@ -524,7 +557,7 @@ __global__ void __launch_bounds__(256) dc_output_kernel(const int* __restrict__ 
 
 }  // namespace
 
-int dw_stedc(Handle* h, Mask mask) {
+int dw_stedc(Handle* h, Mask mask, bool ph, int c_lo) {
   const int n = h->n, B = h->B;
   // both ping-pong buffers start from zero: merges read the off-diagonal blocks of their input
   DW_CUDA(h, cudaMemsetAsync(h->Z0, 0, sizeof(double) * (size_t)n * n * B, h->stream));
@@ -541,6 +574,7 @@ int dw_stedc(Handle* h, Mask mask) {
     DW_CUDA(h, cudaFuncSetAttribute(dc_zhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     DW_CUDA(h, cudaFuncSetAttribute(dc_secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     DW_CUDA(h, cudaFuncSetAttribute(dc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DW_CUDA(h, cudaFuncSetAttribute(dc_halfflag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set[h->device & 63] = true;
   }
   double* Zin = h->Z0;
@@ -575,6 +609,12 @@ int dw_stedc(Handle* h, Mask mask) {
       dc_zhat_kernel<<<grid, 128, (size_t)mm * 24, h->stream>>>(g);
       DW_LAUNCH_CHECK(h);
     }
+    const bool last = (l + 1 == h->levels.size()) && lv.nmerge == 1;
+    const bool skip_low = last && ph && h->ph_mode && c_lo > 0;
+    if (skip_low) {
+      dc_halfflag_kernel<<<B, 256, (size_t)n * 8, h->stream>>>(h->dnew, h->halfflag, n, 1, mask);
+      DW_LAUNCH_CHECK(h);
+    }
     {
       dim3 grid((mm + 7) / 8, lv.nmerge, B);
       dc_vectors_kernel<<<grid, 256, 0, h->stream>>>(g);
@@ -584,6 +624,8 @@ int dw_stedc(Handle* h, Mask mask) {
       GemmArgs ga;
       ga.lv = g;
       ga.ntiles_n = (mm + GBN - 1) / GBN;
+      ga.halfflag = h->halfflag;
+      ga.c_lo = skip_low ? c_lo : 0;
       dim3 grid((mm + GBM - 1) / GBM, lv.nmerge * ga.ntiles_n, B);
       dc_gemm2_kernel<<<grid, 256, G_SMEM, h->stream>>>(ga);
       DW_LAUNCH_CHECK(h);
@@ -599,13 +641,10 @@ int dw_stedc(Handle* h, Mask mask) {
   return DWHMC_OK;
 }
 
-int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph) {
+int dw_stedc_output(Handle* h, double* E_out, cplx* U_out, Mask mask, bool ph, int c_lo) {
   dc_evals_kernel<<<h->B, 256, 0, h->stream>>>(h->d, h->perm, E_out, h->halfflag, h->n, (ph && h->ph_mode) ? 1 : 0, mask);
   DW_LAUNCH_CHECK(h);
   dim3 grid(h->n, h->B);
-  // the GEMM tiles of the back-transformation are at most 128 columns wide: keep every column a
-  // straddling tile may touch
-  const int c_lo = (h->N / 128) * 128;
   dc_output_kernel<<<grid, 256, 0, h->stream>>>(h->perm, h->Zfinal, U_out, h->halfflag, c_lo, h->n, mask);
   DW_LAUNCH_CHECK(h);
   return DWHMC_OK;
