@@ -264,3 +264,32 @@ def test_band_route_against_oracle(dw, monkeypatch, L, B):
         assert abs(dH[b] - dH_r) <= RTOL * max(abs(Ho), 1.0)
         assert bool(acc[b]) == a_r
     cb.close()
+
+
+def test_eigensolve_is_bit_reproducible_at_bench_shape(dw):
+    """Race check by determinism (compute-sanitizer is not available on the GPU pool): the bulge chase pipelines the
+    sweeps of a chain over several CTAs through release/acquire counters and the back-transformation hands work items
+    to CTAs by ticket, so the schedule differs from run to run -- the result must not.  Three eigensolves of the same
+    64 matrices at L = 24 (all 148 CTAs busy in both kernels) have to agree bit for bit, eigenvectors included."""
+    L, B = 24, 64
+    N = L * L
+    rng = np.random.default_rng(77)
+    w = np.zeros((B, N))
+    for b in range(B):
+        w[b, rng.permutation(N)[:29]] = 1.0
+    delta = (rng.random((B, 2, N)) - 0.5 + 1j * (rng.random((B, 2, N)) - 0.5)) * 0.1
+    cb = dw.ChainBatch(B, L, L)
+    cb.set_params(PHYS["t"], PHYS["tp"], PHYS["mu"], np.logspace(-1, 3, B), PHYS["J"], PHYS["mass"])
+    cb.set_disorder(w); cb.set_field(delta)
+    cb.init_static_H(); cb.update_H_BdG()
+    ref = None
+    for _ in range(3):
+        cb.diagonalize_H_BdG()
+        E = cb.get_eigenvalues()
+        U = cb.get_eigenvectors()[::7].copy()          # every 7th chain: 10 x 21 MB
+        if ref is None:
+            ref = (E, U)
+        else:
+            assert np.array_equal(E, ref[0])
+            assert np.array_equal(U.view(np.float64), ref[1].view(np.float64))
+    cb.close()
