@@ -305,7 +305,9 @@ def run_ours(args):
     route = ("band (free dense->band stage: folded site order; bulge chase chase_tmah_kernel, D&C dc_*_kernel + DMMA dc_gemm2_kernel, "
              "register-resident DMMA block reflectors band_apply2_kernel)" if bw else
              "dense (hetrd: hemv_reg_kernel + DMMA zgemm her2k, D&C, DMMA back-transformation)")
-    stages = {"tridiagonalize (band route: bulge chase)": tm["tridiagonalize_ms"], "tridiagonal D&C": tm["stedc_ms"],
+    stages = {("tridiagonalize (band route: bulge chase, chase_tmah_kernel)" if bw else
+               "tridiagonalize (dense route: hemv_reg_kernel + column steps + DMMA her2k)"): tm["tridiagonalize_ms"],
+              "tridiagonal D&C": tm["stedc_ms"],
               "back-transformation": tm["backtransform_ms"]}
     dom_name = max(stages, key=stages.get)
 
@@ -350,7 +352,8 @@ def run_ours(args):
             pass
         dominant = {"kernel": dom_name, "stage_ms_per_batched_eigensolve": stages[dom_name] / n_solves,
                     "share_of_eigensolve": stages[dom_name] / eig_ms,
-                    "bound": "latency (per-step dependency chain; neither FP64 pipe, shared memory, L2 nor HBM saturated)",
+                    "bound": ("latency (per-step dependency chain; neither FP64 pipe, shared memory, L2 nor HBM saturated)" if bw else
+                              "hbm (the trailing-matrix product A v of the one-stage reduction: 1 flop per byte)"),
                     "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "DRAM bytes cannot be measured outside a profiler; see ncu_reference for the committed capture"}
         if ncu_ref and bw and "chase" in ncu_ref:
