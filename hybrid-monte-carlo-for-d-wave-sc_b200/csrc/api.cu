@@ -91,8 +91,8 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
                  const int64_t* nnn_table) {
   if (!out) { g_create_err = "dwhmc_create: out is NULL"; return DWHMC_E_BADARG; }
   *out = nullptr;
-  if (B < 1 || Lx < 3 || Ly < 3 || !nn_table || !nnn_table) {
-    g_create_err = "dwhmc_create: need B >= 1, Lx, Ly >= 3 (distinct neighbours) and both neighbour tables";
+  if (B < 1 || B > 32767 || Lx < 3 || Ly < 3 || !nn_table || !nnn_table) {
+    g_create_err = "dwhmc_create: need 1 <= B <= 32767, Lx, Ly >= 3 (distinct neighbours) and both neighbour tables";
     return DWHMC_E_BADARG;
   }
   int ndev = 0;

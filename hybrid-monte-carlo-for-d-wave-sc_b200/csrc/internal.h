@@ -20,7 +20,9 @@
 #endif
 // DW_GSPLIT: K pieces of the Gram-matrix GEMMs of the back-transformation
 #define DW_NBT 64         // reflectors per block of the eigenvector back-transformation
-#define DW_LEAF 36        // largest D&C leaf
+#ifndef DW_LEAF
+#define DW_LEAF 18        // largest D&C leaf (18: one more merge level than 36, but the QL leaf stage is 4x shorter; 11.08 -> 10.84 ms at L = 24)
+#endif
 #define DW_NGROUP 4       // max chain groups (streams) of the tridiagonalisation
 #define DW_APPLY_G 32      // reflectors per staircase block of the band route's back-transformation
 #define DW_APPLY_ROWS 136  // rows of such a block (half-bandwidth + DW_APPLY_G - 1 at most)
