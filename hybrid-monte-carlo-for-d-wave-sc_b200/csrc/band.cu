@@ -92,6 +92,14 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// polling: relaxed loads while spinning (an acquire load invalidates the SM's L1 on every iteration and holds up the
+// load/store pipe the compute warps are using), one acquire fence once the value is there
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // ---- assembly into band storage ------------------------------------------------------------------
 // pos[r]: band index of row r of the reference's matrix (r < N particle of site r, r >= N hole)
@@ -569,10 +577,11 @@ __global__ void __launch_bounds__(chase_nc(TR, TC) + 32, 1) chase_tmah_kernel(Ch
           if (s > 0) {
             const int need = k + 2;
             sw[2] = 0;                                 // spin count (in shared memory: the kernel has no register to spare);
-            while (ld_acquire(prog + s - 1) < need) {  // bounded: a lost neighbour ends in an error code, not a hang
+            while (ld_relaxed(prog + s - 1) < need) {  // bounded: a lost neighbour ends in an error code, not a hang
               __nanosleep(20);
               if (++sw[2] > (1 << 24)) { atomicExch(g.status + 2, 1); break; }
             }
+            fence_acq();
           }
           if (k > 0) {
             // the corner element is fetched while the last piece of the block is still landing
@@ -1117,6 +1126,8 @@ __global__ void band_de_kernel(const cplx* __restrict__ ABall, double* __restric
 }  // namespace
 
 bool dw_band_has_tma_kernel(int bw);
+bool dw_band_has_systolic_kernel(int bw);
+int dw_band_chase_systolic(Handle* h, Mask mask);
 
 // ring fold: positions 0, L-1, 1, L-2, ... -> consecutive indices
 static std::vector<int> fold_positions(int L) {
@@ -1232,6 +1243,18 @@ int dw_band_assemble(Handle* h, const double* w, const double* par3, const cplx*
 static std::mutex g_chase_mutex;
 static cudaEvent_t g_chase_done[64] = {};
 
+// one guarded cooperative launch (band_systolic.cu)
+int dw_chase_launch_guarded(Handle* h, const void* kern, int nctas, int nthreads, void** args, size_t smem) {
+  std::lock_guard<std::mutex> lock(g_chase_mutex);
+  cudaEvent_t& done = g_chase_done[h->device & 63];
+  if (!done) DW_CUDA(h, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+  else DW_CUDA(h, cudaStreamWaitEvent(h->stream, done, 0));
+  struct Rec { cudaEvent_t e; cudaStream_t s; ~Rec() { cudaEventRecord(e, s); } } rec{done, h->stream};
+  DW_CUDA(h, cudaLaunchCooperativeKernel(kern, dim3(nctas), dim3(nthreads), args, smem, h->stream));
+  h->launches++;
+  return DWHMC_OK;
+}
+
 // launch helper: P persistent CTAs per chain, all co-resident (cooperative launch), chains in slices if needed
 template <class Launch>
 static int chase_launch_loop(Handle* h, Mask mask, const void* kern, int nthreads, size_t smem, bool tickets, Launch launch) {
@@ -1330,7 +1353,17 @@ int dw_band_chase(Handle* h, Mask mask) {
   // DWHMC_BAND_GENERIC=1: the generic chase kernel (any half-bandwidth <= 101, load/store units instead of TMA) -- the
   // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
-  if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
+  // Small batches (at most two position tasks per SM) go to the position-owning kernel of band_systolic.cu: one chain
+  // finishes in n steps instead of 2 n (14.5 instead of 30.5 ms at L = 24, up to 12 chains; even at 32 chains); with more
+  // chains the sweep-owning kernel below keeps every SM busy and wins (64 chains: 45.6 against 56 ms).
+  // DWHMC_CHASE=systolic | sweep forces one of them.
+  static const char* which = getenv("DWHMC_CHASE");
+  const bool has_sys = dw_band_has_systolic_kernel(bw);
+  bool use_sys = has_sys && (long long)B * ((n - 2) / bw + 1) <= 2LL * h->nsm;
+  if (which && which[0] == 's' && which[1] == 'y') use_sys = has_sys;
+  if (which && which[0] == 's' && which[1] == 'w') use_sys = false;
+  if (!generic && use_sys) DW_TRY(dw_band_chase_systolic(h, mask));
+  else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
   else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
   else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
   else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));

@@ -1,0 +1,739 @@
+// band_systolic.cu -- position-owning ("systolic") bulge chase of the band route of diagonalize_H_BdG!
+// (/root/reference src/Hamiltonian.jl:96-114; the reference calls LAPACK zheevr there).
+//
+// Same algorithm, reflectors, tau and tridiagonal matrix as chase_tmah_kernel in band.cu (Lang's bulge chasing:
+// sweep s, step k, reflector on rows r0 .. r0+b-1, r0 = s + 1 + k b), but the work is cut the other way: a CTA owns
+// step k ("position" k) of EVERY sweep of a chain instead of every step of one sweep.  The two b x b blocks of a
+// step -- the carried block Bc (rows r0.., columns r0-b..) and the diagonal block D -- then only slide down the
+// diagonal by one row and one column per sweep, so they never leave the SM:
+//   * element (global row g, global column c) of a window lives at the physical slot (g mod b, c mod b); a slide
+//     overwrites one physical row and one physical column, nothing else moves.  Vectors are indexed the same way.
+//   * Bc lives in registers (RB x CB elements per thread, compile-time indices), D in shared memory with both
+//     triangles (a torus has no fixed lower triangle), rows / columns beyond the matrix are kept at zero, so the
+//     block operations carry no length masks.
+//   * per sweep a position exchanges O(b) numbers with its neighbours through their true places in global memory:
+//       k-1 -> k   the reflector v(s, k-1) and tau (the V / tau outputs the back-transformation needs anyway)
+//       k+1 -> k   row 0 of Bc(s-1, k+1) after its update (new last row of D(s, k) and the corner of Bc(s, k)) and
+//                  the corner D(s-1, k+1)[0, 0], both written to the band storage AB
+//     guarded by three release / acquire counters per (chain, position): vflag, bflag, dflag = sweeps published.
+//     The column that leaves D on a slide becomes the new last column of Bc (position 0: the next column to
+//     annihilate).  Position 0 also delivers the tridiagonal matrix (d, e) into AB where band_de_kernel reads it.
+//   * a helper warp does everything that waits on the memory system: it polls the neighbours' counters, brings
+//     their messages into (double-buffered) shared memory ahead of time and publishes this position's counters;
+//     the compute warps meet it at named barriers only.
+// Global traffic per step drops from 3 b^2 elements (two tensor copies and the diagonal block through L2) to ~4 b.
+// Tasks (chain, position) are handed out by one ticket counter in (chain, position) order: whoever waits for a
+// neighbour waits for a task with a smaller ticket or for the next untaken ones, which the CTAs of finished
+// positions pick up, so the cooperative launch cannot deadlock.
+// NumPy prototype of exactly this organisation: tests/algo_proto_systolic.py (checked against the sweep-owning
+// prototype and LAPACK in tests/test_algo_proto.py).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "dwhmc.h"
+#include "internal.h"
+
+namespace {
+
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {       // acc += a b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfms(cplx& acc, cplx a, cplx b) {       // acc -= a b
+  acc.x = fma(-a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfmac(cplx& acc, cplx a, cplx b) {      // acc += conj(a) b
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ cplx warp_sum(cplx v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+// everything the positions of a chain exchange goes through L2 (no stale L1 lines)
+__device__ __forceinline__ cplx ldg2(const cplx* p) {
+  cplx v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg2(cplx* p, cplx v) {
+  asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin with relaxed loads (an acquire load invalidates the SM's L1 on every poll), one fence after success
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+#ifndef LDS2_VOLATILE
+#define LDS2_VOLATILE volatile
+#endif
+// shared-memory load the compiler may not hoist or merge (keeps streamed vector entries out of the register file)
+__device__ __forceinline__ cplx lds2(const cplx* p) {
+  cplx v;
+  asm LDS2_VOLATILE("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+// bulk-copy engine (TMA): the helper warp brings the neighbours' messages in with it, so no global load of the
+// helper sits in the load/store pipe the compute warps read shared memory through
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct SysArgs {
+  cplx* AB; cplx* V; cplx* tau2;
+  cplx* rowbox;                  // [B][KT][2][TB+2]: row message of (chain, position), slot = sweep & 1: row 0 of the updated Bc, then the corner of D
+  int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k; then [1] task ticket
+  int n, LD, KT, KP, B;          // KP: positions per chain
+  int* status;                   // device status words: [2] set when a wait timed out
+  Mask mask;
+  long long* clk;                // optional [8] phase clocks of one position (experiments, -DDWHMC_CHASE_PROF)
+};
+
+// named barriers: 1 compute threads only; the others are shared with the helper warp (NC + 32 threads)
+enum { BAR_VP = 2, BAR_ROW = 3, BAR_VW = 4, BAR_RW = 5, BAR_TASK = 6 };
+template <int NC> __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
+template <int NC> __device__ __forceinline__ void hbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NC + 32) : "memory"); }
+template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NC + 32) : "memory");
+}
+__host__ __device__ constexpr int sys_nc(int tr, int tc) { return (tr * tc + 31) / 32 * 32; }
+// rows of the partial sums of z = v^H Bc: neighbouring lanes (rows ri, ri+1 of one thread column) are added by a
+// shuffle first when TR is even
+__host__ __device__ constexpr int sys_zrows(int tr) { return (tr % 2 == 0) ? tr / 2 : tr; }
+
+template <int TB, int TR, int TC>
+constexpr size_t sys_smem() {
+  // D [TB][TB], partial sums [zrows + TC][TB+1], 10 vectors (vp x2, rowmsg x2, vs, xs, tu, wc, ys, xcol), red[32], 8 scalars, control
+  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 9 * TB + 2 + 32 + 10) + 64;
+}
+
+// One step of a position (sweep s), compute warps:
+//   P1  u = Bc vp (partial sums per thread column)                                  [needs v of position k-1]
+//   P2  u, x = Bc[:,0] - taup u, |x|^2; the row / column that entered D last sweep   [needs the row message of k+1]
+//   P3  reflector: tau, beta, v                                  -> V, tau2, (e) to global, vflag published
+//   P4  z = v^H Bc (registers) and y = D v (shared memory), partial sums
+//   P5  wc = conj(tau) z, y = tau D v, y^H v
+//   P6  w = y + alpha v; the first row of the updated Bc (the row message) ahead of the update itself
+//   P7  row message and corner to global, rflag published; Bc -= tu vp^H + v wc, D -= v w^H + w v^H
+//   P8  slide
+template <int TB, int TR, int TC, int RB, int CB>
+__global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysArgs g) {
+  constexpr int NC = sys_nc(TR, TC);
+  static_assert(TR * RB == TB && TC * CB >= TB && TC * (CB - 1) < TB, "cover of the b x b windows (rows exactly)");
+  constexpr bool XC = TC * CB == TB;             // exact column cover; otherwise the last column of a thread may not exist
+#define JV(cc) (XC || (cc) < CB - 1 || cj + (cc) * TC < TB)
+  constexpr int LPE = (NC >= 4 * TB) ? 4 : ((NC >= 2 * TB) ? 2 : 1);   // lanes per entry of a matrix-vector product
+  static_assert(NC >= TB && NC + 32 <= 1024, "one thread per vector entry at least");
+  constexpr bool ZPAIR = TR % 2 == 0;
+  constexpr int ZR = sys_zrows(TR);
+  constexpr int LDD = TB;
+  constexpr int LDP = TB + 1;    // partial sums: odd leading dimension
+  extern __shared__ __align__(16) unsigned char smem_sys[];
+  cplx* D = reinterpret_cast<cplx*>(smem_sys);       // [TB][LDD] physical column-major, both triangles
+  cplx* partz = D + TB * LDD;                        // [ZR][LDP] partial sums of z (column TB: v^H tu)
+  cplx* party = partz + ZR * LDP;                    // [TC][LDP] partial sums of u, then of y
+  cplx* vpbuf = party + TC * LDP;                    // [2][TB] previous reflector (physical column index)
+  cplx* rowbuf = vpbuf + 2 * TB;                     // [2][TB+1] row message of position k+1: row, corner
+  cplx* vs = rowbuf + 2 * (TB + 1);
+  cplx* xs = vs + TB;
+  cplx* tu = xs + TB;
+  cplx* wc = tu + TB;
+  cplx* ys = xs;                                     // (x is dead after the reflector, y is born in P5)
+  cplx* xcol = wc + TB;
+  cplx* red = xcol + TB;                             // [32]
+  cplx* scal = red + 32;                             // [10]: taup[2], -, -, tau, beta, -, -, poll buffer, mbarrier
+  volatile int* sw = reinterpret_cast<volatile int*>(scal + 10);   // [2] chain, position of the task just taken (-1: none left)
+  const int tid = threadIdx.x;
+  const int n = g.n, LD = g.LD, KT = g.KT;
+  const cplx zero = make_double2(0.0, 0.0);
+  int* const ticket = g.flags + (size_t)n * g.B;
+
+  if (tid >= NC) {
+    // ================= helper warp =================
+    const int lane = tid - NC;
+    const bool l0 = lane == 0;
+    bool dead = false;                               // a wait timed out: stop waiting, let the launch drain
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(scal + 9);   // completion barrier of the helper's bulk copies
+    cplx* pollbuf = scal + 8;                        // 16 bytes: the counters around the one being polled
+    unsigned ph = 0;
+    if (l0) {
+      mbar_init(mb, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // wait until *flag >= need: the 16-byte chunk around the counter is fetched by the bulk-copy engine again and again
+    // (a polling load in the load/store pipe would stall the shared-memory loads of the compute warps behind it)
+    auto wait_for = [&](const int* flag, int need) {
+      if (l0 && !dead) {
+        const int* chunk = reinterpret_cast<const int*>(reinterpret_cast<unsigned long long>(flag) & ~15ull);
+        const int off = (int)(flag - chunk);
+        int spins = 0;
+        for (;;) {
+          fence_async();
+          mbar_expect_tx(mb, 16);
+          bulk_load(pollbuf, chunk, 16, mb);
+          mbar_wait(mb, ph); ph ^= 1;
+          if (reinterpret_cast<volatile int*>(pollbuf)[off] >= need) break;
+          __nanosleep(40);
+          if (++spins > (1 << 20) || ((spins & 255) == 0 && *((volatile int*)g.status + 2) != 0)) {
+            atomicExch(g.status + 2, 1);
+            dead = true;
+            break;
+          }
+        }
+      }
+      __syncwarp();
+    };
+    for (;;) {
+      int chain = 0, k = -1;
+      if (l0) {
+        for (;;) {
+          const int t = atomicAdd(ticket, 1);
+          if (t >= g.B * g.KP) break;
+          const int c = t / g.KP;
+          if (!g.mask.on(c)) continue;
+          chain = c; k = t - c * g.KP;
+          break;
+        }
+        sw[0] = chain; sw[1] = k;
+      }
+      chain = __shfl_sync(0xffffffffu, chain, 0);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      hbar_arrive<NC>(BAR_TASK);
+      if (k < 0) return;
+      cplx* AB = g.AB + (size_t)chain * n * LD;
+      int* fl = g.flags + (size_t)chain * n;
+      const int nsteps = n - 1 - k * TB;
+      int r0 = 1 + k * TB, o = r0 % TB;
+      for (int s = 0; s < nsteps; ++s) {
+        const int buf = s & 1;
+        // ---- inputs of step s: v and tau of position k-1 (the columns of Bc always exist) ...
+        if (k > 0) {
+          wait_for(fl + (k - 1), s + 1);
+          if (l0) {
+            const cplx* Vseg = g.V + ((size_t)chain * n + s) * n + (r0 - TB);
+            cplx* dst = vpbuf + buf * TB;
+            fence_async();
+            mbar_expect_tx(mb, (unsigned)((TB + 1) * sizeof(cplx)));
+            if (o > 0) {                             // logical index l -> physical (o + l) mod TB: two pieces
+              bulk_load(dst + o, Vseg, (unsigned)((TB - o) * sizeof(cplx)), mb);
+              bulk_load(dst, Vseg + (TB - o), (unsigned)(o * sizeof(cplx)), mb);
+            } else {
+              bulk_load(dst, Vseg, (unsigned)(TB * sizeof(cplx)), mb);
+            }
+            bulk_load(scal + buf, g.tau2 + ((size_t)chain * n + s) * KT + (k - 1), (unsigned)sizeof(cplx), mb);
+            mbar_wait(mb, ph); ph ^= 1;
+          }
+          __syncwarp();
+        }
+        hbar_arrive<NC>(BAR_VP);
+        // ... and the row message of position k+1 (sweep s-1): row 0 of its updated Bc, then the corner of its D
+        cplx* rdst = rowbuf + buf * (TB + 1);
+        if (r0 + TB - 1 < n) {                       // the row / column that entered the windows exists
+          if (s > 0) {
+            wait_for(fl + KT + (k + 1), s);
+            if (l0) {
+              fence_async();
+              mbar_expect_tx(mb, (unsigned)((TB + 1) * sizeof(cplx)));
+              bulk_load(rdst, g.rowbox + (((size_t)chain * KT + (k + 1)) * 2 + ((s - 1) & 1)) * (TB + 2),
+                        (unsigned)((TB + 1) * sizeof(cplx)), mb);
+              mbar_wait(mb, ph); ph ^= 1;
+            }
+            __syncwarp();
+          } else {                                   // first sweep: still in the band storage
+            for (int j = lane; j < TB; j += 32) rdst[j] = ldg2(AB + (size_t)(r0 - 1 + j) * LD + (TB - j));
+            if (l0) rdst[TB] = ldg2(AB + (size_t)(r0 + TB - 1) * LD);
+          }
+        } else {
+          for (int j = lane; j <= TB; j += 32) rdst[j] = zero;
+        }
+        hbar_arrive<NC>(BAR_ROW);
+        // ---- outputs of step s
+        hbar_sync<NC>(BAR_VW);
+        if (l0) { __threadfence(); st_release(fl + k, s + 1); }
+        hbar_sync<NC>(BAR_RW);
+        if (l0) { __threadfence(); st_release(fl + KT + k, s + 1); }
+        ++r0;
+        o = (o + 1 == TB) ? 0 : o + 1;
+      }
+    }
+  }
+
+  // ================= compute threads =================
+  const bool act = tid < TR * TC;
+  const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
+  const int ei = tid / LPE, esl = tid % LPE;         // LPE lanes per entry of a matrix-vector product
+  auto sumL = [&](const cplx* part, int col, int nq, bool valid) -> cplx {   // sum_q part[q][col], q < nq; result in all LPE lanes
+    cplx a = zero;
+    if (valid)
+      for (int q = esl; q < nq; q += LPE) a = cadd(a, part[q * LDP + col]);
+    if (LPE >= 2) { a.x += __shfl_xor_sync(0xffffffffu, a.x, 1); a.y += __shfl_xor_sync(0xffffffffu, a.y, 1); }
+    if (LPE >= 4) { a.x += __shfl_xor_sync(0xffffffffu, a.x, 2); a.y += __shfl_xor_sync(0xffffffffu, a.y, 2); }
+    return a;
+  };
+  auto red_sum = [&]() -> cplx {                             // sum of the per-warp partials, four independent chains
+    cplx a0 = zero, a1 = zero, a2 = zero, a3 = zero;
+#pragma unroll
+    for (int w = 0; w < NC / 32; w += 4) {
+      a0 = cadd(a0, red[w]);
+      if (w + 1 < NC / 32) a1 = cadd(a1, red[w + 1]);
+      if (w + 2 < NC / 32) a2 = cadd(a2, red[w + 2]);
+      if (w + 3 < NC / 32) a3 = cadd(a3, red[w + 3]);
+    }
+    return cadd(cadd(a0, a1), cadd(a2, a3));
+  };
+#ifdef DWHMC_CHASE_PROF
+  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  bool prof = false;
+#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
+  for (;;) {
+    hbar_sync<NC>(BAR_TASK);
+    const int chain = sw[0], k = sw[1];
+    if (k < 0) break;
+#ifdef DWHMC_CHASE_PROF
+    if (prof) { for (int i = 0; i < 8; ++i) g.clk[i] = tph[i]; }
+    prof = g.clk != nullptr && tid == 0 && chain == 0 && k == DWHMC_CHASE_PROF;
+    if (prof) tlast = clock64();
+#endif
+    cplx* AB = g.AB + (size_t)chain * n * LD;
+    const int nsteps = n - 1 - k * TB;
+    int r0 = 1 + k * TB, o = r0 % TB;
+    cplx Bc[RB][CB];
+#pragma unroll
+    for (int cc = 0; cc < CB; ++cc)
+#pragma unroll
+      for (int q = 0; q < RB; ++q) Bc[q][cc] = zero;
+    // ---- windows of sweep 0 from the band storage (the physical row / column that "just entered" is patched
+    //      from the messages of the first step like in every later one)
+    {
+      const int po = (o == 0) ? TB - 1 : o - 1;
+#pragma unroll
+      for (int cc = 0; cc < CB; ++cc) {
+        if (!JV(cc)) continue;
+        const int pc = cj + cc * TC;
+        const int lc = pc - o + (pc < o ? TB : 0);
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          const int pr = ri + q * TR;
+          const int gr = r0 + pr - o + (pr < o ? TB : 0);
+          const bool rowok = act && gr < n && pr != po;
+          {
+            const int gc = r0 - TB + lc;
+            Bc[q][cc] = (rowok && k > 0) ? ldg2(AB + (size_t)gc * LD + (gr - gc)) : zero;
+          }
+          if (act) {
+            const int gc = r0 + lc;
+            cplx a = zero;
+            if (rowok && gc < n && pc != po) {
+              if (gr >= gc) a = ldg2(AB + (size_t)gc * LD + (gr - gc));
+              else a = cconj(ldg2(AB + (size_t)gr * LD + (gc - gr)));
+              if (gr == gc) a.y = 0.0;
+            }
+            D[pc * LDD + pr] = a;
+          }
+        }
+      }
+      if (k == 0)
+        for (int p = tid; p < TB; p += NC) {
+          const int gr = r0 + p - o + (p < o ? TB : 0);
+          xcol[p] = (gr < n && p != po) ? ldg2(AB + gr) : zero;       // column 0, rows 1 ..: AB[0 * LD + gr]
+        }
+    }
+    csync<NC>();
+    for (int s = 0; s < nsteps; ++s) {
+      const int po = (o == 0) ? TB - 1 : o - 1;      // physical index of the row / column that entered last
+      const int buf = s & 1;
+      const cplx* vp = vpbuf + buf * TB;
+      const cplx* rowm = rowbuf + buf * (TB + 1);
+      // ---- P1: u = Bc vp (the new last row of Bc is still zero; its corner comes with the row message)
+      hbar_sync<NC>(BAR_VP);
+      PH(0);
+      if (k > 0 && act) {
+        cplx acc[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          if (!JV(cc)) continue;
+          const int pc = cj + cc * TC;
+          const cplx vj = vp[pc];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) cfma(acc[q], Bc[q][cc], vj);
+          if (pc == o) {                              // logical column 0: the column to annihilate (before the update)
+#pragma unroll
+            for (int q = 0; q < RB; ++q) xcol[ri + q * TR] = Bc[q][cc];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+      }
+      csync<NC>();
+      PH(1);
+      hbar_sync<NC>(BAR_ROW);
+      PH(2);
+      // ---- P2: u, x and its norm; the row / column that entered D (its corner is added in P5)
+      {
+        double nrm2 = 0.0;
+        if (k > 0) {
+          cplx u = sumL(party, ei, TC, ei < TB);
+          if (esl == 0 && ei < TB) {
+            if (ei == po) cfma(u, rowm[0], vp[po]);
+            const cplx t = cmul(scal[buf], u);
+            tu[ei] = t;
+            const cplx x = csub(xcol[ei], t);
+            xs[ei] = x;
+            if (ei != o) nrm2 = x.x * x.x + x.y * x.y;
+          }
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < RB; ++q)
+              if (ri + q * TR == po) {
+#pragma unroll
+                for (int cc = 0; cc < CB; ++cc)
+                  if (cj + cc * TC == po) Bc[q][cc] = rowm[0];
+              }
+          }
+        } else {
+          for (int p = tid; p < TB; p += NC) {
+            const cplx x = (p == po) ? rowm[0] : xcol[p];
+            xs[p] = x;
+            if (p != o) nrm2 += x.x * x.x + x.y * x.y;
+          }
+        }
+        for (int p = tid; p < TB; p += NC) {
+          if (p != po) {
+            const int j = p - po + (p < po ? TB : 0);
+            const cplx val = rowm[j];
+            D[p * LDD + po] = val;                      // row po, column p
+            D[po * LDD + p] = cconj(val);
+          } else {
+            D[po * LDD + po] = zero;
+          }
+        }
+        nrm2 = warp_sum(make_double2(nrm2, 0.0)).x;
+        if ((tid & 31) == 0) red[tid >> 5] = make_double2(nrm2, 0.0);
+      }
+      csync<NC>();
+      // ---- P3: reflector (LAPACK zlarfg; every thread computes tau, beta and the scale)
+      const bool flush = k > 0 && n - r0 <= 1;       // nothing to annihilate: only the pending right-application
+      {
+        cplx tau, betac;
+        const double nrm = red_sum().x;
+        const cplx alpha = xs[o];
+        cplx scale;
+        if (flush) {
+          betac = alpha; tau = zero; scale = zero;
+        } else if (nrm == 0.0 && alpha.y == 0.0) {
+          betac = make_double2(alpha.x, 0.0); tau = zero; scale = zero;
+        } else {
+          const double beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm), alpha.x);
+          const double dr = alpha.x - beta, di = alpha.y;
+          const double ibeta = 1.0 / beta, iden = 1.0 / (dr * dr + di * di);   // two independent divisions
+          tau = make_double2(-dr * ibeta, -di * ibeta);
+          scale = make_double2(dr * iden, -di * iden);
+          betac = make_double2(beta, 0.0);
+        }
+        for (int p = tid; p < TB; p += NC) vs[p] = (p == o) ? make_double2(1.0, 0.0) : cmul(xs[p], scale);
+        if (tid == 0) { scal[4] = tau; scal[5] = betac; }   // later phases re-read them (registers are scarce)
+      }
+      csync<NC>();
+      {
+        cplx* Vcol = g.V + ((size_t)chain * n + s) * n + r0;
+        for (int p = tid; p < TB; p += NC) {
+          const int lg = p - o + (p < o ? TB : 0);
+          if (r0 + lg < n) stg2(Vcol + lg, flush ? zero : vs[p]);
+        }
+        if (tid == 0) {
+          stg2(g.tau2 + ((size_t)chain * n + s) * KT + k, lds2(scal + 4));
+          if (k == 0) stg2(AB + (size_t)s * LD + 1, lds2(scal + 5));   // e[s]
+        }
+      }
+      hbar_arrive<NC>(BAR_VW);
+      PH(3);
+      // ---- P4: z = v^H Bc (registers) and y = D v (shared memory): partial sums
+      //      (the shuffles are executed by whole warps: idle threads of the last warp hold a zero block)
+      if (k > 0) {
+        cplx vr[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) vr[q] = vs[ri + q * TR];
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          cplx acc = zero;
+#pragma unroll
+          for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], Bc[q][cc]);
+          if (ZPAIR) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (act && JV(cc) && (ri & 1) == 0) partz[(ri >> 1) * LDP + cj + cc * TC] = acc;
+          } else if (act && JV(cc)) {
+            partz[ri * LDP + cj + cc * TC] = acc;
+          }
+        }
+        {
+          cplx acc = zero;                             // v^H tu rides along as column TB (thread column 0 only)
+#pragma unroll
+          for (int q = 0; q < RB; ++q) cfmac(acc, vr[q], tu[ri + q * TR]);
+          if (ZPAIR) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (act && cj == 0 && (ri & 1) == 0) partz[(ri >> 1) * LDP + TB] = acc;
+          } else if (act && cj == 0) {
+            partz[ri * LDP + TB] = acc;
+          }
+        }
+      }
+      if (act) {
+        {
+          cplx acc[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const int pc = cj + cc * TC;
+            const cplx vj = vs[pc];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) cfma(acc[q], D[pc * LDD + ri + q * TR], vj);
+          }
+#pragma unroll
+          for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+        }
+      }
+      csync<NC>();
+      PH(4);
+      // ---- P5: wc = conj(tau) z, y = tau D v (with the corner that entered), y^H v
+      {
+        const cplx tau = lds2(scal + 4);
+        cplx dot = zero;
+        if (k > 0) {
+          cplx z = sumL(partz, ei, ZR, ei < TB);
+          const cplx c = sumL(partz, TB, ZR, true);
+          if (esl == 0 && ei < TB) {
+            cfms(z, c, cconj(vp[ei]));
+            wc[ei] = cmul(cconj(tau), z);
+          }
+        }
+        cplx y = sumL(party, ei, TC, ei < TB);
+        if (esl == 0 && ei < TB) {
+          if (ei == po) {
+            const double corner = rowm[TB].x;
+            const cplx vpo = vs[po];
+            y.x = fma(corner, vpo.x, y.x); y.y = fma(corner, vpo.y, y.y);
+            D[po * LDD + po] = make_double2(corner, 0.0);
+          }
+          y = cmul(tau, y);
+          ys[ei] = y;
+          cfmac(dot, y, vs[ei]);
+        }
+        dot = warp_sum(dot);
+        if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
+      }
+      csync<NC>();
+      // ---- P6: w = y + alpha v (zhetd2), in place; row r0 of the updated Bc (the row message) ahead of the update
+      {
+        cplx alpha2 = cmul(lds2(scal + 4), red_sum());
+        alpha2.x *= -0.5; alpha2.y *= -0.5;
+        for (int p = tid; p < TB; p += NC) { cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w; }
+        if (k > 0 && act) {
+#pragma unroll
+          for (int q = 0; q < RB; ++q)
+            if (ri + q * TR == o) {
+              const cplx tq = tu[o];                    // v[o] = 1
+              const cplx bt = lds2(scal + 5);
+#pragma unroll
+              for (int cc = 0; cc < CB; ++cc) {
+                if (!JV(cc)) continue;
+                const int j = cj + cc * TC;
+                cplx a = Bc[q][cc];
+                cfms(a, tq, cconj(vp[j]));
+                a = csub(a, wc[j]);
+                xcol[j] = (j == o) ? bt : a;
+              }
+            }
+        }
+      }
+      csync<NC>();
+      PH(5);
+      // ---- P7: messages out, then the two block updates
+      {
+        cplx* box = g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2);
+        if (k > 0) {
+          for (int p = tid; p < TB; p += NC) stg2(box + (p - o + (p < o ? TB : 0)), xcol[p]);   // row r0 of Bc, logical column order
+        }
+        if (tid == 0) {
+          // corner message: D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band storage
+          const cplx c = make_double2(D[o * LDD + o].x - 2.0 * ys[o].x, 0.0);
+          if (k > 0) stg2(box + TB, c);
+          else stg2(AB + (size_t)r0 * LD, c);
+        }
+      }
+      hbar_arrive<NC>(BAR_RW);
+      if (act) {
+        // column by column: the row operands (v, w, tu of this thread's RB rows) stay in registers, the column operands
+        // are broadcast loads; the register-only update of Bc covers the latency of the shared-memory update of D
+        cplx vq[RB], wq[RB], tq[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) { vq[q] = vs[ri + q * TR]; wq[q] = ys[ri + q * TR]; tq[q] = tu[ri + q * TR]; }
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          if (!JV(cc)) continue;
+          const int j = cj + cc * TC;
+          cplx dq[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) dq[q] = lds2(D + j * LDD + ri + q * TR);
+          if (k > 0) {
+            const cplx cvp = cconj(lds2(vp + j)), wj = lds2(wc + j);
+#pragma unroll
+            for (int q = 0; q < RB; ++q) { cfms(Bc[q][cc], tq[q], cvp); cfms(Bc[q][cc], vq[q], wj); }
+          }
+          const cplx cwj = cconj(lds2(ys + j)), cvj = cconj(lds2(vs + j));
+#pragma unroll
+          for (int q = 0; q < RB; ++q) {
+            cfms(dq[q], vq[q], cwj);
+            cfms(dq[q], wq[q], cvj);
+            if (ri + q * TR == j) dq[q].y = 0.0;
+            D[j * LDD + ri + q * TR] = dq[q];
+          }
+        }
+      }
+      csync<NC>();
+      PH(6);
+      // ---- P8 slide: the column that leaves D is the new last column of Bc (position 0: the next column to
+      //      annihilate); the row that leaves makes room for the new last row (zero until its message arrives).
+      //      (Logical column 0 of Bc, annihilated by this step, is the one that is overwritten.)
+      if (k > 0) {
+        if (act) {
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc)
+            if (cj + cc * TC == o) {
+#pragma unroll
+              for (int q = 0; q < RB; ++q) Bc[q][cc] = D[o * LDD + ri + q * TR];
+            }
+#pragma unroll
+          for (int q = 0; q < RB; ++q)
+            if (ri + q * TR == o) {
+#pragma unroll
+              for (int cc = 0; cc < CB; ++cc) Bc[q][cc] = zero;
+            }
+        }
+      } else {
+        for (int p = tid; p < TB; p += NC) xcol[p] = (p == o) ? zero : D[o * LDD + p];
+      }
+      ++r0;
+      o = (o + 1 == TB) ? 0 : o + 1;
+      PH(7);
+    }
+  }
+#ifdef DWHMC_CHASE_PROF
+  if (prof) { for (int i = 0; i < 8; ++i) g.clk[i] = tph[i]; }
+#endif
+#undef PH
+#undef JV
+}
+
+}  // namespace
+
+// launch serialisation shared with the sweep-owning kernels (band.cu): chase launches wait on each other
+int dw_chase_launch_guarded(Handle* h, const void* kern, int nctas, int nthreads, void** args, size_t smem);
+
+template <int TB, int TR, int TC, int RB, int CB>
+static int sys_dispatch(Handle* h, Mask mask) {
+  const int nthreads = sys_nc(TR, TC) + 32;
+  const size_t smem = sys_smem<TB, TR, TC>();
+  const void* kern = (const void*)chase_sys_kernel<TB, TR, TC, RB, CB>;
+  static bool attr[64] = {false};
+  if (!attr[h->device & 63]) {
+    DW_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[h->device & 63] = true;
+  }
+  int per_sm = 0;
+  DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
+  if (per_sm < 1) { h->err = "dw_band_chase_systolic: kernel does not fit"; return DWHMC_E_CUDA; }
+  SysArgs a;
+  a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.flags = h->band_prog; a.rowbox = h->band_rowbox;
+  a.n = h->n; a.LD = h->band_LD; a.KT = h->band_KT; a.KP = (h->n - 2) / TB + 1; a.B = h->B;
+  a.status = h->status; a.mask = mask; a.clk = nullptr;
+  const int nctas = std::min(h->nsm * per_sm, h->B * a.KP);
+  void* args[] = {&a};
+#ifdef DWHMC_CHASE_PROF                                  // phase clocks of position DWHMC_CHASE_PROF of chain 0 (experiments)
+  static long long* clk_dev = nullptr;
+  if (!clk_dev) { cudaMalloc(&clk_dev, 8 * sizeof(long long)); cudaMemset(clk_dev, 0, 8 * sizeof(long long)); }
+  a.clk = clk_dev;
+  DW_TRY(dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem));
+  long long c[8];
+  cudaStreamSynchronize(h->stream);
+  cudaMemcpy(c, clk_dev, sizeof(c), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "systolic phase kclk/step [waitV u waitRow P2+P3 P4 P5+P6 P7 slide]: %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f (steps %d)\n",
+          c[0] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[1] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[2] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB),
+          c[3] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[4] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[5] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB),
+          c[6] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[7] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), h->n - 1 - DWHMC_CHASE_PROF * TB);
+  return DWHMC_OK;
+#else
+  return dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem);
+#endif
+}
+
+bool dw_band_has_systolic_kernel(int bw) {
+  switch (bw) {
+    case 100: case 84: case 76: case 68: case 60: case 52: case 44: case 36: case 28: return true;
+    default: return false;
+  }
+}
+
+// h->A (band) -> reflectors h->V, h->band_tau; the tridiagonal matrix is left in the band storage (band_de_kernel)
+int dw_band_chase_systolic(Handle* h, Mask mask) {
+  switch (h->band_b) {
+    case 100: return sys_dispatch<100, 50, 7, 2, 15>(h, mask);   // 2 x 15 elements per thread: the row operands of an update fit next to the block
+    case 84: return sys_dispatch<84, 21, 16, 4, 6>(h, mask);
+    case 76: return sys_dispatch<76, 19, 19, 4, 4>(h, mask);
+    case 68: return sys_dispatch<68, 17, 17, 4, 4>(h, mask);
+    case 60: return sys_dispatch<60, 15, 20, 4, 3>(h, mask);
+    case 52: return sys_dispatch<52, 13, 26, 4, 2>(h, mask);
+    case 44: return sys_dispatch<44, 22, 11, 2, 4>(h, mask);
+    case 36: return sys_dispatch<36, 18, 18, 2, 2>(h, mask);
+    case 28: return sys_dispatch<28, 14, 14, 2, 2>(h, mask);
+    default: h->err = "dw_band_chase_systolic: no kernel for this half-bandwidth"; return DWHMC_E_BADARG;
+  }
+}

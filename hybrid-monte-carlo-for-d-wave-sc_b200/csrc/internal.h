@@ -135,6 +135,7 @@ struct Handle {
   int* band_pos = nullptr;      // device [n]: band index of row r of the reference's matrix
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
+  cplx* band_rowbox = nullptr;  // device [B][KT][2][b+2]: row messages of the position-owning chase (band_systolic.cu)
   cplx* band_VT = nullptr;      // device, DW_APPLY_BLOCK_DOUBLES doubles per (chain, block): conj(V) and -V T, operand planes of the back-transformation
   int band_nitems = 0;                    // work items per chain of the back-transformation (blocks x column parts, wavefront order)
   int band_apply_attr = 0;                // row tiles of the apply kernel instance whose shared-memory attribute is set

@@ -56,3 +56,23 @@ def test_band_route_prototype_matches_lapack():
         scale = np.max(np.abs(w))
         assert np.max(np.abs(d2 - d)) <= 1e-12 * scale and np.max(np.abs(e2 - e)) <= 1e-12 * scale
         assert np.max(np.abs(V2 - V)) <= 1e-11 and np.max(np.abs(TAU2 - TAU)) <= 1e-11
+
+
+def test_systolic_chase_prototype_matches_sweep_owning_prototype():
+    """tests/algo_proto_systolic.py (the organisation of csrc/band_systolic.cu: a position owns step k of every
+    sweep; windows slide on a torus, messages travel through the band storage) produces the same tridiagonal
+    matrix, reflectors and tau as the sweep-owning prototype, on matrices whose order is / is not a multiple of the
+    half-bandwidth, with one position only, and with a band as wide as the matrix allows."""
+    import algo_proto_band as apb
+    import algo_proto_systolic as aps
+    rng = np.random.default_rng(1)
+    for n, b in ((23, 4), (40, 7), (37, 5), (30, 28), (64, 12), (50, 3), (72, 28)):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        A = A + A.conj().T
+        i, j = np.indices((n, n))
+        A[np.abs(i - j) > b] = 0
+        d0, e0, V0, T0 = apb.chase_band(A, b)
+        d1, e1, V1, T1 = aps.chase_systolic(A, b)
+        scale = np.max(np.abs(A))
+        assert np.max(np.abs(d0 - d1)) <= 1e-12 * scale and np.max(np.abs(e0 - e1)) <= 1e-12 * scale
+        assert np.max(np.abs(V0 - V1)) <= 1e-11 and np.max(np.abs(T0 - T1)) <= 1e-11
