@@ -752,18 +752,30 @@ def test_default_route_is_band_where_a_chase_kernel_exists(dw):
         cb.close()
 
 
-@pytest.mark.parametrize("switch", ["DWHMC_BAND_GENERIC=1"])
+CHASE_SWITCH_SHAPES = {
+    # the generic kernel (load/store units): L = 8 (b = 36) and a rectangle whose half-bandwidth is rounded up (24 -> 28)
+    "DWHMC_BAND_GENERIC=1": (["8", "3"], ["5x13", "2"]),
+    # the position-owning kernel forced on batches it is not the default for: more position tasks than CTAs (the
+    # ticket queue hands finished CTAs the next positions), at L = 8 (600 tasks) and at L = 24 (16 chains, 192 tasks)
+    "DWHMC_CHASE=systolic": (["8", "150"], ["24", "16"], ["9", "40"]),
+    # the sweep-owning kernel forced on the small batches the position-owning one is the default for
+    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"]),
+}
+
+
+@pytest.mark.parametrize("switch", sorted(CHASE_SWITCH_SHAPES))
 def test_chase_fallback_kernels(switch):
-    """The one fallback of the band route behind its (process-wide, read-once) switch -- the generic bulge-chase
-    kernel on the load/store units -- against LAPACK, in a process of its own: eigenvalues, residual and unitarity of
-    chains at L = 8 (b = 36) and of a rectangular lattice whose half-bandwidth is rounded up (5 x 13: 24 -> 28)."""
+    """The bulge-chase kernels behind their (process-wide, read-once) switches against LAPACK, each in a process of its
+    own: eigenvalues, residual and unitarity of two chains per shape.  By default small batches run the position-owning
+    kernel (band_systolic.cu) and large ones the sweep-owning kernel (band.cu); every other GPU test therefore covers
+    one of the two at its own batch size, this one covers the other."""
     import re
     import subprocess
     import sys
     key, val = switch.split("=")
     env = dict(os.environ, **{key: val})
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for args in (["8", "3"], ["5x13", "2"]):
+    for args in CHASE_SWITCH_SHAPES[switch]:
         out = subprocess.run([sys.executable, os.path.join(root, "tools", "band_check.py")] + args, env=env,
                              capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
