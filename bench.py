@@ -377,8 +377,10 @@ def run_ours(args):
                              "api": "reference_api.hmc_sweep + measure_observables, one chain per handle: the call sequence of the "
                                     "unchanged reference scripts (scripts/test_simulation.jl:25-31)",
                              "cpu_1_process_all_threads": cpu_modes.get("as_shipped_1proc_all_threads"),
-                             "note": "one chain cannot fill the GPU: the sweeps of the bulge chase of one matrix are two steps "
-                                     "apart, ~31 ms per eigensolve however many SMs help; batch chains (ChainBatch) for throughput"},
+                             "note": "one chain cannot fill the GPU: small batches run the position-owning bulge chase "
+                                     "(band_systolic.cu, 12 CTAs per chain at L = 24, one sweep per step time: ~15 ms per "
+                                     "eigensolve instead of ~31 with the sweep-owning kernel); batch chains (ChainBatch) for "
+                                     "throughput"},
             "gpu_launches": launches,
             "clocks": clk.summary(),
             # the dense eigensolve (A3) sits on the FP64 tensor (DMMA) roofline, 40/3 n^3 flops per matrix
