@@ -122,7 +122,7 @@ __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;
 struct SysArgs {
   cplx* AB; cplx* V; cplx* tau2;
   cplx* rowbox;                  // [B][KT][2][TB+2]: row message of (chain, position), slot = sweep & 1: row 0 of the updated Bc, then the corner of D
-  int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k; then [1] task ticket
+  int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k, dflag[k] at 2 KT + k; then [1] task ticket
   int n, LD, KT, KP, B;          // KP: positions per chain
   int* status;                   // device status words: [2] set when a wait timed out
   Mask mask;
@@ -130,7 +130,7 @@ struct SysArgs {
 };
 
 // named barriers: 1 compute threads only; the others are shared with the helper warp (NC + 32 threads)
-enum { BAR_VP = 2, BAR_ROW = 3, BAR_VW = 4, BAR_RW = 5, BAR_TASK = 6 };
+enum { BAR_VP = 2, BAR_ROW = 3, BAR_CORNER = 4, BAR_VW = 5, BAR_RW = 6, BAR_DW = 7, BAR_TASK = 8 };
 template <int NC> __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NC + 32) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
@@ -225,6 +225,14 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       __syncwarp();
     };
+    auto probe = [&](const int* flag, int need) -> int {   // lane 0: one look at a counter
+      const int* chunk = reinterpret_cast<const int*>(reinterpret_cast<unsigned long long>(flag) & ~15ull);
+      fence_async();
+      mbar_expect_tx(mb, 16);
+      bulk_load(pollbuf, chunk, 16, mb);
+      mbar_wait(mb, ph); ph ^= 1;
+      return reinterpret_cast<volatile int*>(pollbuf)[(int)(flag - chunk)] >= need ? 1 : 0;
+    };
     for (;;) {
       int chain = 0, k = -1;
       if (l0) {
@@ -268,16 +276,17 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           __syncwarp();
         }
         hbar_arrive<NC>(BAR_VP);
-        // ... and the row message of position k+1 (sweep s-1): row 0 of its updated Bc, then the corner of its D
+        // ... the row message of position k+1 (sweep s-1): row 0 of its updated Bc ...
         cplx* rdst = rowbuf + buf * (TB + 1);
-        if (r0 + TB - 1 < n) {                       // the row / column that entered the windows exists
+        const bool newrow = r0 + TB - 1 < n;         // the row / column that entered the windows exists
+        const cplx* box_in = g.rowbox + (((size_t)chain * KT + (k + 1)) * 2 + ((s - 1) & 1)) * (TB + 2);
+        if (newrow) {
           if (s > 0) {
             wait_for(fl + KT + (k + 1), s);
             if (l0) {
               fence_async();
-              mbar_expect_tx(mb, (unsigned)((TB + 1) * sizeof(cplx)));
-              bulk_load(rdst, g.rowbox + (((size_t)chain * KT + (k + 1)) * 2 + ((s - 1) & 1)) * (TB + 2),
-                        (unsigned)((TB + 1) * sizeof(cplx)), mb);
+              mbar_expect_tx(mb, (unsigned)(TB * sizeof(cplx)));
+              bulk_load(rdst, box_in, (unsigned)(TB * sizeof(cplx)), mb);
               mbar_wait(mb, ph); ph ^= 1;
             }
             __syncwarp();
@@ -289,11 +298,36 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           for (int j = lane; j <= TB; j += 32) rdst[j] = zero;
         }
         hbar_arrive<NC>(BAR_ROW);
-        // ---- outputs of step s
+        // ---- outputs of step s, and (when it is there) the corner of D(s-1, k+1), needed last
         hbar_sync<NC>(BAR_VW);
         if (l0) { __threadfence(); st_release(fl + k, s + 1); }
+        auto fetch_corner = [&]() {
+          if (l0) {
+            fence_async();
+            mbar_expect_tx(mb, (unsigned)sizeof(cplx));
+            bulk_load(rdst + TB, box_in + TB, (unsigned)sizeof(cplx), mb);
+            mbar_wait(mb, ph); ph ^= 1;
+          }
+          __syncwarp();
+        };
+        const bool need_corner = newrow && s > 0;
+        bool have_corner = !need_corner;
+        if (need_corner) {                           // one look: do not hold up the row message of this step for it
+          int ready = 0;
+          if (l0) ready = probe(fl + 2 * KT + (k + 1), s);
+          ready = __shfl_sync(0xffffffffu, ready, 0);
+          if (ready) { fetch_corner(); have_corner = true; }
+        }
+        if (have_corner) hbar_arrive<NC>(BAR_CORNER);
         hbar_sync<NC>(BAR_RW);
         if (l0) { __threadfence(); st_release(fl + KT + k, s + 1); }
+        if (!have_corner) {
+          wait_for(fl + 2 * KT + (k + 1), s);
+          fetch_corner();
+          hbar_arrive<NC>(BAR_CORNER);
+        }
+        hbar_sync<NC>(BAR_DW);
+        if (l0) { __threadfence(); st_release(fl + 2 * KT + k, s + 1); }
         ++r0;
         o = (o + 1 == TB) ? 0 : o + 1;
       }
@@ -494,9 +528,10 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       hbar_arrive<NC>(BAR_VW);
       PH(3);
-      // ---- P4: z = v^H Bc (registers) and y = D v (shared memory): partial sums
-      //      (the shuffles are executed by whole warps: idle threads of the last warp hold a zero block)
+      // ---- P4a-P6a (positions k > 0): z = v^H Bc, wc = conj(tau) z, and row r0 of the updated Bc -- the row message
+      //      position k-1 is waiting for -- ahead of everything that does not feed it
       if (k > 0) {
+        // (the shuffles are executed by whole warps: idle threads of the last warp hold a zero block)
         cplx vr[RB];
 #pragma unroll
         for (int q = 0; q < RB; ++q) vr[q] = vs[ri + q * TR];
@@ -523,60 +558,17 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
             partz[ri * LDP + TB] = acc;
           }
         }
-      }
-      if (act) {
+        csync<NC>();
         {
-          cplx acc[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) acc[q] = zero;
-#pragma unroll
-          for (int cc = 0; cc < CB; ++cc) {
-            if (!JV(cc)) continue;
-            const int pc = cj + cc * TC;
-            const cplx vj = vs[pc];
-#pragma unroll
-            for (int q = 0; q < RB; ++q) cfma(acc[q], D[pc * LDD + ri + q * TR], vj);
-          }
-#pragma unroll
-          for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
-        }
-      }
-      csync<NC>();
-      PH(4);
-      // ---- P5: wc = conj(tau) z, y = tau D v (with the corner that entered), y^H v
-      {
-        const cplx tau = lds2(scal + 4);
-        cplx dot = zero;
-        if (k > 0) {
           cplx z = sumL(partz, ei, ZR, ei < TB);
           const cplx c = sumL(partz, TB, ZR, true);
           if (esl == 0 && ei < TB) {
             cfms(z, c, cconj(vp[ei]));
-            wc[ei] = cmul(cconj(tau), z);
+            wc[ei] = cmul(cconj(lds2(scal + 4)), z);
           }
         }
-        cplx y = sumL(party, ei, TC, ei < TB);
-        if (esl == 0 && ei < TB) {
-          if (ei == po) {
-            const double corner = rowm[TB].x;
-            const cplx vpo = vs[po];
-            y.x = fma(corner, vpo.x, y.x); y.y = fma(corner, vpo.y, y.y);
-            D[po * LDD + po] = make_double2(corner, 0.0);
-          }
-          y = cmul(tau, y);
-          ys[ei] = y;
-          cfmac(dot, y, vs[ei]);
-        }
-        dot = warp_sum(dot);
-        if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
-      }
-      csync<NC>();
-      // ---- P6: w = y + alpha v (zhetd2), in place; row r0 of the updated Bc (the row message) ahead of the update
-      {
-        cplx alpha2 = cmul(lds2(scal + 4), red_sum());
-        alpha2.x *= -0.5; alpha2.y *= -0.5;
-        for (int p = tid; p < TB; p += NC) { cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w; }
-        if (k > 0 && act) {
+        csync<NC>();
+        if (act) {
 #pragma unroll
           for (int q = 0; q < RB; ++q)
             if (ri + q * TR == o) {
@@ -593,23 +585,67 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
               }
             }
         }
-      }
-      csync<NC>();
-      PH(5);
-      // ---- P7: messages out, then the two block updates
-      {
-        cplx* box = g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2);
-        if (k > 0) {
-          for (int p = tid; p < TB; p += NC) stg2(box + (p - o + (p < o ? TB : 0)), xcol[p]);   // row r0 of Bc, logical column order
-        }
-        if (tid == 0) {
-          // corner message: D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band storage
-          const cplx c = make_double2(D[o * LDD + o].x - 2.0 * ys[o].x, 0.0);
-          if (k > 0) stg2(box + TB, c);
-          else stg2(AB + (size_t)r0 * LD, c);
+        csync<NC>();
+        {
+          cplx* box = g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2);
+          for (int p = tid; p < TB; p += NC) stg2(box + (p - o + (p < o ? TB : 0)), xcol[p]);   // logical column order
         }
       }
       hbar_arrive<NC>(BAR_RW);
+      PH(4);
+      // ---- P4b: y = D v (shared memory), partial sums
+      if (act) {
+        cplx acc[RB];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) acc[q] = zero;
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          if (!JV(cc)) continue;
+          const int pc = cj + cc * TC;
+          const cplx vj = vs[pc];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) cfma(acc[q], D[pc * LDD + ri + q * TR], vj);
+        }
+#pragma unroll
+        for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+      }
+      csync<NC>();
+      hbar_sync<NC>(BAR_CORNER);
+      // ---- P5b: y = tau D v (with the corner that entered), y^H v
+      {
+        cplx dot = zero;
+        cplx y = sumL(party, ei, TC, ei < TB);
+        if (esl == 0 && ei < TB) {
+          if (ei == po) {
+            const double corner = rowm[TB].x;
+            const cplx vpo = vs[po];
+            y.x = fma(corner, vpo.x, y.x); y.y = fma(corner, vpo.y, y.y);
+            D[po * LDD + po] = make_double2(corner, 0.0);
+          }
+          y = cmul(lds2(scal + 4), y);
+          ys[ei] = y;
+          cfmac(dot, y, vs[ei]);
+        }
+        dot = warp_sum(dot);
+        if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
+      }
+      csync<NC>();
+      // ---- P6b: w = y + alpha v (zhetd2), in place
+      {
+        cplx alpha2 = cmul(lds2(scal + 4), red_sum());
+        alpha2.x *= -0.5; alpha2.y *= -0.5;
+        for (int p = tid; p < TB; p += NC) { cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w; }
+      }
+      csync<NC>();
+      PH(5);
+      // ---- P7: corner message out, then the two block updates
+      if (tid == 0) {
+        // D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band storage
+        const cplx c = make_double2(D[o * LDD + o].x - 2.0 * ys[o].x, 0.0);
+        if (k > 0) stg2(g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2) + TB, c);
+        else stg2(AB + (size_t)r0 * LD, c);
+      }
+      hbar_arrive<NC>(BAR_DW);
       if (act) {
         // column by column: the row operands (v, w, tu of this thread's RB rows) stay in registers, the column operands
         // are broadcast loads; the register-only update of Bc covers the latency of the shared-memory update of D
