@@ -1353,14 +1353,12 @@ int dw_band_chase(Handle* h, Mask mask) {
   // DWHMC_BAND_GENERIC=1: the generic chase kernel (any half-bandwidth <= 101, load/store units instead of TMA) -- the
   // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
-  // Small batches (at most two position tasks per SM) go to the position-owning kernel of band_systolic.cu: one chain
-  // finishes in n steps instead of 2 n (14.5 instead of 30.5 ms at L = 24, up to 12 chains; even at 32 chains); with more
-  // chains the sweep-owning kernel below keeps every SM busy and wins (64 chains: 45.6 against 56 ms).
-  // DWHMC_CHASE=systolic | sweep forces one of them.
+  // Default wherever it has an instance: the position-owning kernel of band_systolic.cu (one chain finishes in n step
+  // times instead of 2 n, and the blocks never leave the SM: 12.2 instead of 30.5 ms for up to 12 chains at L = 24,
+  // 38.3 instead of 46 ms for 64).  DWHMC_CHASE=sweep forces the sweep-owning TMA kernel below, the band route's
+  // second kernel.
   static const char* which = getenv("DWHMC_CHASE");
-  const bool has_sys = dw_band_has_systolic_kernel(bw);
-  bool use_sys = has_sys && (long long)B * ((n - 2) / bw + 1) <= 2LL * h->nsm;
-  if (which && which[0] == 's' && which[1] == 'y') use_sys = has_sys;
+  bool use_sys = dw_band_has_systolic_kernel(bw);
   if (which && which[0] == 's' && which[1] == 'w') use_sys = false;
   if (!generic && use_sys) DW_TRY(dw_band_chase_systolic(h, mask));
   else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));

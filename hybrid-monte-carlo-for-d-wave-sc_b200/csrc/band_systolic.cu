@@ -122,15 +122,16 @@ __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;
 struct SysArgs {
   cplx* AB; cplx* V; cplx* tau2;
   cplx* rowbox;                  // [B][KT][2][TB+2]: row message of (chain, position), slot = sweep & 1: row 0 of the updated Bc, then the corner of D
-  int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k, dflag[k] at 2 KT + k; then [1] task ticket
+  int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k, dflag[k] at 2 KT + k, sflag[k] (epochs saved) at 3 KT + k; then [1] task ticket
   int n, LD, KT, KP, B;          // KP: positions per chain
+  int Q, NE;                     // sweeps per epoch, epochs: a task = (epoch, chain, position), handed out in this order
   int* status;                   // device status words: [2] set when a wait timed out
   Mask mask;
   long long* clk;                // optional [8] phase clocks of one position (experiments, -DDWHMC_CHASE_PROF)
 };
 
 // named barriers: 1 compute threads only; the others are shared with the helper warp (NC + 32 threads)
-enum { BAR_VP = 2, BAR_ROW = 3, BAR_CORNER = 4, BAR_VW = 5, BAR_RW = 6, BAR_DW = 7, BAR_TASK = 8 };
+enum { BAR_VP = 2, BAR_ROW = 3, BAR_CORNER = 4, BAR_VW = 5, BAR_RW = 6, BAR_DW = 7, BAR_TASK = 8, BAR_SAVE = 9 };
 template <int NC> __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NC + 32) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   cplx* xcol = wc + TB;
   cplx* red = xcol + TB;                             // [32]
   cplx* scal = red + 32;                             // [10]: taup[2], -, -, tau, beta, -, -, poll buffer, mbarrier
-  volatile int* sw = reinterpret_cast<volatile int*>(scal + 10);   // [2] chain, position of the task just taken (-1: none left)
+  volatile int* sw = reinterpret_cast<volatile int*>(scal + 10);   // [3] chain, position (-1: none left), epoch of the task just taken
   const int tid = threadIdx.x;
   const int n = g.n, LD = g.LD, KT = g.KT;
   const cplx zero = make_double2(0.0, 0.0);
@@ -234,27 +235,35 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       return reinterpret_cast<volatile int*>(pollbuf)[(int)(flag - chunk)] >= need ? 1 : 0;
     };
     for (;;) {
-      int chain = 0, k = -1;
+      int chain = 0, k = -1, ep = 0;
       if (l0) {
         for (;;) {
-          const int t = atomicAdd(ticket, 1);
-          if (t >= g.B * g.KP) break;
-          const int c = t / g.KP;
+          int t = atomicAdd(ticket, 1);
+          int e = 0, kpe = 0;
+          for (; e < g.NE; ++e) {                    // tasks of epoch e: B x (positions alive at sweep e Q)
+            kpe = (n - 2 - e * g.Q) / TB + 1;
+            if (t < g.B * kpe) break;
+            t -= g.B * kpe;
+          }
+          if (e >= g.NE) break;
+          const int c = t / kpe;
           if (!g.mask.on(c)) continue;
-          chain = c; k = t - c * g.KP;
+          chain = c; k = t - c * kpe; ep = e;
           break;
         }
-        sw[0] = chain; sw[1] = k;
+        sw[0] = chain; sw[1] = k; sw[2] = ep;
       }
       chain = __shfl_sync(0xffffffffu, chain, 0);
       k = __shfl_sync(0xffffffffu, k, 0);
-      hbar_arrive<NC>(BAR_TASK);
-      if (k < 0) return;
+      ep = __shfl_sync(0xffffffffu, ep, 0);
       cplx* AB = g.AB + (size_t)chain * n * LD;
       int* fl = g.flags + (size_t)chain * n;
-      const int nsteps = n - 1 - k * TB;
-      int r0 = 1 + k * TB, o = r0 % TB;
-      for (int s = 0; s < nsteps; ++s) {
+      if (k >= 0 && ep > 0) wait_for(fl + 3 * KT + k, ep);   // the windows of this position as the previous epoch left them
+      hbar_arrive<NC>(BAR_TASK);
+      if (k < 0) return;
+      const int s0 = ep * g.Q, s1 = min((ep + 1) * g.Q, n - 1 - k * TB);
+      int r0 = s0 + 1 + k * TB, o = r0 % TB;
+      for (int s = s0; s < s1; ++s) {
         const int buf = s & 1;
         // ---- inputs of step s: v and tau of position k-1 (the columns of Bc always exist) ...
         if (k > 0) {
@@ -331,6 +340,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         ++r0;
         o = (o + 1 == TB) ? 0 : o + 1;
       }
+      hbar_sync<NC>(BAR_SAVE);                         // windows written back (if the position goes on in the next epoch)
+      if (l0 && s1 < n - 1 - k * TB) { __threadfence(); st_release(fl + 3 * KT + k, ep + 1); }
     }
   }
 
@@ -374,8 +385,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     if (prof) tlast = clock64();
 #endif
     cplx* AB = g.AB + (size_t)chain * n * LD;
-    const int nsteps = n - 1 - k * TB;
-    int r0 = 1 + k * TB, o = r0 % TB;
+    const int s0 = sw[2] * g.Q, s1 = min((sw[2] + 1) * g.Q, n - 1 - k * TB);
+    int r0 = s0 + 1 + k * TB, o = r0 % TB;
     cplx Bc[RB][CB];
 #pragma unroll
     for (int cc = 0; cc < CB; ++cc)
@@ -414,11 +425,11 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       if (k == 0)
         for (int p = tid; p < TB; p += NC) {
           const int gr = r0 + p - o + (p < o ? TB : 0);
-          xcol[p] = (gr < n && p != po) ? ldg2(AB + gr) : zero;       // column 0, rows 1 ..: AB[0 * LD + gr]
+          xcol[p] = (gr < n && p != po) ? ldg2(AB + (size_t)(r0 - 1) * LD + (gr - (r0 - 1))) : zero;   // column s0 below the diagonal
         }
     }
     csync<NC>();
-    for (int s = 0; s < nsteps; ++s) {
+    for (int s = s0; s < s1; ++s) {
       const int po = (o == 0) ? TB - 1 : o - 1;      // physical index of the row / column that entered last
       const int buf = s & 1;
       const cplx* vp = vpbuf + buf * TB;
@@ -701,6 +712,38 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       o = (o + 1 == TB) ? 0 : o + 1;
       PH(7);
     }
+    // ---- end of the epoch: if the position goes on, its windows go back to the band storage for whichever CTA takes
+    //      the next epoch (the row / column that entered last is still on its way as a message and is not written)
+    if (s1 < n - 1 - k * TB) {
+      const int po = (o == 0) ? TB - 1 : o - 1;
+      if (k == 0) {
+        for (int p = tid; p < TB; p += NC) {
+          const int gr = r0 + p - o + (p < o ? TB : 0);
+          if (gr < n && p != po) stg2(AB + (size_t)(r0 - 1) * LD + (gr - (r0 - 1)), xcol[p]);
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int cc = 0; cc < CB; ++cc) {
+          if (!JV(cc)) continue;
+          const int pc = cj + cc * TC;
+          const int lc = pc - o + (pc < o ? TB : 0);
+#pragma unroll
+          for (int q = 0; q < RB; ++q) {
+            const int pr = ri + q * TR;
+            const int gr = r0 + pr - o + (pr < o ? TB : 0);
+            if (gr >= n || pr == po) continue;
+            if (k > 0) {
+              const int gc = r0 - TB + lc;
+              stg2(AB + (size_t)gc * LD + (gr - gc), Bc[q][cc]);
+            }
+            const int gc = r0 + lc;
+            if (gc <= gr && pc != po) stg2(AB + (size_t)gc * LD + (gr - gc), D[pc * LDD + pr]);
+          }
+        }
+      }
+    }
+    hbar_arrive<NC>(BAR_SAVE);
   }
 #ifdef DWHMC_CHASE_PROF
   if (prof) { for (int i = 0; i < 8; ++i) g.clk[i] = tph[i]; }
@@ -731,6 +774,12 @@ static int sys_dispatch(Handle* h, Mask mask) {
   a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.flags = h->band_prog; a.rowbox = h->band_rowbox;
   a.n = h->n; a.LD = h->band_LD; a.KT = h->band_KT; a.KP = (h->n - 2) / TB + 1; a.B = h->B;
   a.status = h->status; a.mask = mask; a.clk = nullptr;
+  // Epochs: with more position tasks than CTAs a chain is cut into epochs of Q sweeps, so that the CTAs the short
+  // positions of early chains set free go to later chains at once and every chain ends at about the same time (one
+  // epoch per chain would leave the last chain running alone for n step times).  Small batches: a single epoch.
+  a.Q = (h->B * a.KP <= h->nsm * per_sm) ? h->n : std::max(32, 5 * TB / 4);
+  if (const char* e = getenv("DWHMC_CHASE_Q")) a.Q = std::max(8, atoi(e));
+  a.NE = (h->n - 1 + a.Q - 1) / a.Q;
   const int nctas = std::min(h->nsm * per_sm, h->B * a.KP);
   void* args[] = {&a};
 #ifdef DWHMC_CHASE_PROF                                  // phase clocks of position DWHMC_CHASE_PROF of chain 0 (experiments)

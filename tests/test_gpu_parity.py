@@ -755,20 +755,21 @@ def test_default_route_is_band_where_a_chase_kernel_exists(dw):
 CHASE_SWITCH_SHAPES = {
     # the generic kernel (load/store units): L = 8 (b = 36) and a rectangle whose half-bandwidth is rounded up (24 -> 28)
     "DWHMC_BAND_GENERIC=1": (["8", "3"], ["5x13", "2"]),
-    # the position-owning kernel forced on batches it is not the default for: more position tasks than CTAs (the
-    # ticket queue hands finished CTAs the next positions), at L = 8 (600 tasks) and at L = 24 (16 chains, 192 tasks)
-    "DWHMC_CHASE=systolic": (["8", "150"], ["24", "16"], ["9", "40"]),
-    # the sweep-owning kernel forced on the small batches the position-owning one is the default for
-    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"]),
+    # the position-owning kernel (the default) with short epochs: every position changes CTAs every 16 / 37 sweeps
+    # through the band storage, at L = 8 with more tasks than CTAs, at L = 24, and on a rectangle
+    "DWHMC_CHASE_Q=16": (["8", "150"], ["24", "3"], ["5x13", "2"]),
+    "DWHMC_CHASE_Q=37": (["16", "40"], ["6x10", "3"]),
+    # the sweep-owning kernel (band.cu), the band route's second kernel
+    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"], ["8", "150"]),
 }
 
 
 @pytest.mark.parametrize("switch", sorted(CHASE_SWITCH_SHAPES))
 def test_chase_fallback_kernels(switch):
     """The bulge-chase kernels behind their (process-wide, read-once) switches against LAPACK, each in a process of its
-    own: eigenvalues, residual and unitarity of two chains per shape.  By default small batches run the position-owning
-    kernel (band_systolic.cu) and large ones the sweep-owning kernel (band.cu); every other GPU test therefore covers
-    one of the two at its own batch size, this one covers the other."""
+    own: eigenvalues, residual and unitarity of two chains per shape.  The default is the position-owning kernel
+    (band_systolic.cu; every other GPU test runs it, with one epoch for small batches and epochs of 5 b / 4 sweeps for
+    large ones); here: short epochs, the sweep-owning kernel (band.cu) and the generic kernel."""
     import re
     import subprocess
     import sys
