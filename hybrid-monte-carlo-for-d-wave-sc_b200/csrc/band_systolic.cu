@@ -146,7 +146,7 @@ __host__ __device__ constexpr int sys_zrows(int tr) { return (tr % 2 == 0) ? tr 
 template <int TB, int TR, int TC>
 constexpr size_t sys_smem() {
   // D [TB][TB], partial sums [zrows + TC][TB+1], 10 vectors (vp x2, rowmsg x2, vs, xs, tu, wc, ys, xcol), red[32], 8 scalars, control
-  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 9 * TB + 2 + 32 + 10) + 64;
+  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 10 * TB + 2 + 32 + 10) + 64;
 }
 
 // One step of a position (sweep s), compute warps:
@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   cplx* wc = tu + TB;
   cplx* ys = xs;                                     // (x is dead after the reflector, y is born in P5)
   cplx* xcol = wc + TB;
-  cplx* red = xcol + TB;                             // [32]
+  cplx* xrow = xcol + TB;                            // row 0 of Bc before the update (for the row message)
+  cplx* red = xrow + TB;                             // [32]
   cplx* scal = red + 32;                             // [10]: taup[2], -, -, tau, beta, -, -, poll buffer, mbarrier
   volatile int* sw = reinterpret_cast<volatile int*>(scal + 10);   // [3] chain, position (-1: none left), epoch of the task just taken
   const int tid = threadIdx.x;
@@ -216,7 +217,6 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           bulk_load(pollbuf, chunk, 16, mb);
           mbar_wait(mb, ph); ph ^= 1;
           if (reinterpret_cast<volatile int*>(pollbuf)[off] >= need) break;
-          __nanosleep(40);
           if (++spins > (1 << 20) || ((spins & 255) == 0 && *((volatile int*)g.status + 2) != 0)) {
             atomicExch(g.status + 2, 1);
             dead = true;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         hbar_arrive<NC>(BAR_ROW);
         // ---- outputs of step s, and (when it is there) the corner of D(s-1, k+1), needed last
         hbar_sync<NC>(BAR_VW);
-        if (l0) { __threadfence(); st_release(fl + k, s + 1); }
+        if (l0) st_release(fl + k, s + 1);             // (a release store is cumulative over what the barrier ordered)
         auto fetch_corner = [&]() {
           if (l0) {
             fence_async();
@@ -329,19 +329,19 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
         if (have_corner) hbar_arrive<NC>(BAR_CORNER);
         hbar_sync<NC>(BAR_RW);
-        if (l0) { __threadfence(); st_release(fl + KT + k, s + 1); }
+        if (l0) st_release(fl + KT + k, s + 1);
         if (!have_corner) {
           wait_for(fl + 2 * KT + (k + 1), s);
           fetch_corner();
           hbar_arrive<NC>(BAR_CORNER);
         }
         hbar_sync<NC>(BAR_DW);
-        if (l0) { __threadfence(); st_release(fl + 2 * KT + k, s + 1); }
+        if (l0) st_release(fl + 2 * KT + k, s + 1);
         ++r0;
         o = (o + 1 == TB) ? 0 : o + 1;
       }
       hbar_sync<NC>(BAR_SAVE);                         // windows written back (if the position goes on in the next epoch)
-      if (l0 && s1 < n - 1 - k * TB) { __threadfence(); st_release(fl + 3 * KT + k, ep + 1); }
+      if (l0 && s1 < n - 1 - k * TB) st_release(fl + 3 * KT + k, ep + 1);
     }
   }
 
@@ -369,9 +369,12 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     return cadd(cadd(a0, a1), cadd(a2, a3));
   };
 #ifdef DWHMC_CHASE_PROF
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+  long long tph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
   bool prof = false;
-#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+// time between barrier RELEASES (a clock read right after BAR.SYNC would capture the issue of the barrier, not its
+// release: the read is made to depend on a shared-memory load behind the barrier)
+#define PH(i) do { if (prof) { const int d_ = *reinterpret_cast<volatile int*>(sw); long long t_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(d_) : "memory"); tph[i] += t_ - tlast; tlast = t_; } } while (0)
 #else
 #define PH(i) do { } while (0)
 #endif
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     const int chain = sw[0], k = sw[1];
     if (k < 0) break;
 #ifdef DWHMC_CHASE_PROF
-    if (prof) { for (int i = 0; i < 8; ++i) g.clk[i] = tph[i]; }
+    if (prof) { for (int i = 0; i < 16; ++i) g.clk[i] = tph[i]; }
     prof = g.clk != nullptr && tid == 0 && chain == 0 && k == DWHMC_CHASE_PROF;
     if (prof) tlast = clock64();
 #endif
@@ -455,6 +458,13 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
 #pragma unroll
         for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+#pragma unroll
+        for (int q = 0; q < RB; ++q)
+          if (ri + q * TR == o) {                     // logical row 0 as it is now: the row message is formed from it in P5a
+#pragma unroll
+            for (int cc = 0; cc < CB; ++cc)
+              if (JV(cc)) xrow[cj + cc * TC] = Bc[q][cc];
+          }
       }
       csync<NC>();
       PH(1);
@@ -503,6 +513,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if ((tid & 31) == 0) red[tid >> 5] = make_double2(nrm2, 0.0);
       }
       csync<NC>();
+      PH(3);
       // ---- P3: reflector (LAPACK zlarfg; every thread computes tau, beta and the scale)
       const bool flush = k > 0 && n - r0 <= 1;       // nothing to annihilate: only the pending right-application
       {
@@ -526,6 +537,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if (tid == 0) { scal[4] = tau; scal[5] = betac; }   // later phases re-read them (registers are scarce)
       }
       csync<NC>();
+      PH(4);
       {
         cplx* Vcol = g.V + ((size_t)chain * n + s) * n + r0;
         for (int p = tid; p < TB; p += NC) {
@@ -538,7 +550,6 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
       }
       hbar_arrive<NC>(BAR_VW);
-      PH(3);
       // ---- P4a-P6a (positions k > 0): z = v^H Bc, wc = conj(tau) z, and row r0 of the updated Bc -- the row message
       //      position k-1 is waiting for -- ahead of everything that does not feed it
       if (k > 0) {
@@ -570,40 +581,27 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           }
         }
         csync<NC>();
+        PH(5);
         {
+          // wc = conj(tau) z, and with it row r0 of the updated Bc -- the row message -- straight to its mailbox:
+          // Bc[0, j] - tu[0] conj(vp[j]) - v[0] wc[j] with v[0] = 1; the annihilated column holds beta
           cplx z = sumL(partz, ei, ZR, ei < TB);
           const cplx c = sumL(partz, TB, ZR, true);
           if (esl == 0 && ei < TB) {
-            cfms(z, c, cconj(vp[ei]));
-            wc[ei] = cmul(cconj(lds2(scal + 4)), z);
+            const cplx cvp = cconj(vp[ei]);
+            cfms(z, c, cvp);
+            const cplx w = cmul(cconj(lds2(scal + 4)), z);
+            wc[ei] = w;
+            cplx a = xrow[ei];
+            cfms(a, tu[o], cvp);
+            a = csub(a, w);
+            if (ei == o) a = lds2(scal + 5);
+            cplx* box = g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2);
+            stg2(box + (ei - o + (ei < o ? TB : 0)), a);   // logical column order
           }
-        }
-        csync<NC>();
-        if (act) {
-#pragma unroll
-          for (int q = 0; q < RB; ++q)
-            if (ri + q * TR == o) {
-              const cplx tq = tu[o];                    // v[o] = 1
-              const cplx bt = lds2(scal + 5);
-#pragma unroll
-              for (int cc = 0; cc < CB; ++cc) {
-                if (!JV(cc)) continue;
-                const int j = cj + cc * TC;
-                cplx a = Bc[q][cc];
-                cfms(a, tq, cconj(vp[j]));
-                a = csub(a, wc[j]);
-                xcol[j] = (j == o) ? bt : a;
-              }
-            }
-        }
-        csync<NC>();
-        {
-          cplx* box = g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2);
-          for (int p = tid; p < TB; p += NC) stg2(box + (p - o + (p < o ? TB : 0)), xcol[p]);   // logical column order
         }
       }
       hbar_arrive<NC>(BAR_RW);
-      PH(4);
       // ---- P4b: y = D v (shared memory), partial sums
       if (act) {
         cplx acc[RB];
@@ -621,7 +619,9 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
       }
       csync<NC>();
+      PH(8);
       hbar_sync<NC>(BAR_CORNER);
+      PH(9);
       // ---- P5b: y = tau D v (with the corner that entered), y^H v
       {
         cplx dot = zero;
@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if ((tid & 31) == 0) red[tid >> 5] = dot;       // red was last read before the barrier that closed the reflector
       }
       csync<NC>();
+      PH(10);
       // ---- P6b: w = y + alpha v (zhetd2), in place
       {
         cplx alpha2 = cmul(lds2(scal + 4), red_sum());
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         for (int p = tid; p < TB; p += NC) { cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w; }
       }
       csync<NC>();
-      PH(5);
+      PH(11);
       // ---- P7: corner message out, then the two block updates
       if (tid == 0) {
         // D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band storage
@@ -667,15 +668,18 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         for (int cc = 0; cc < CB; ++cc) {
           if (!JV(cc)) continue;
           const int j = cj + cc * TC;
+          // every shared-memory operand of the column first, then the arithmetic: one load latency per column
+          cplx cvp = zero, wj = zero;
+          if (k > 0) { cvp = lds2(vp + j); wj = lds2(wc + j); }
           cplx dq[RB];
 #pragma unroll
           for (int q = 0; q < RB; ++q) dq[q] = lds2(D + j * LDD + ri + q * TR);
+          const cplx cwj = cconj(lds2(ys + j)), cvj = cconj(lds2(vs + j));
           if (k > 0) {
-            const cplx cvp = cconj(lds2(vp + j)), wj = lds2(wc + j);
+            cvp = cconj(cvp);
 #pragma unroll
             for (int q = 0; q < RB; ++q) { cfms(Bc[q][cc], tq[q], cvp); cfms(Bc[q][cc], vq[q], wj); }
           }
-          const cplx cwj = cconj(lds2(ys + j)), cvj = cconj(lds2(vs + j));
 #pragma unroll
           for (int q = 0; q < RB; ++q) {
             cfms(dq[q], vq[q], cwj);
@@ -686,7 +690,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
       }
       csync<NC>();
-      PH(6);
+      PH(12);
       // ---- P8 slide: the column that leaves D is the new last column of Bc (position 0: the next column to
       //      annihilate); the row that leaves makes room for the new last row (zero until its message arrives).
       //      (Logical column 0 of Bc, annihilated by this step, is the one that is overwritten.)
@@ -710,7 +714,6 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       ++r0;
       o = (o + 1 == TB) ? 0 : o + 1;
-      PH(7);
     }
     // ---- end of the epoch: if the position goes on, its windows go back to the band storage for whichever CTA takes
     //      the next epoch (the row / column that entered last is still on its way as a message and is not written)
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     hbar_arrive<NC>(BAR_SAVE);
   }
 #ifdef DWHMC_CHASE_PROF
-  if (prof) { for (int i = 0; i < 8; ++i) g.clk[i] = tph[i]; }
+  if (prof) { for (int i = 0; i < 16; ++i) g.clk[i] = tph[i]; }
 #endif
 #undef PH
 #undef JV
@@ -784,16 +787,17 @@ static int sys_dispatch(Handle* h, Mask mask) {
   void* args[] = {&a};
 #ifdef DWHMC_CHASE_PROF                                  // phase clocks of position DWHMC_CHASE_PROF of chain 0 (experiments)
   static long long* clk_dev = nullptr;
-  if (!clk_dev) { cudaMalloc(&clk_dev, 8 * sizeof(long long)); cudaMemset(clk_dev, 0, 8 * sizeof(long long)); }
+  if (!clk_dev) { cudaMalloc(&clk_dev, 16 * sizeof(long long)); cudaMemset(clk_dev, 0, 16 * sizeof(long long)); }
   a.clk = clk_dev;
   DW_TRY(dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem));
-  long long c[8];
+  long long c[16];
   cudaStreamSynchronize(h->stream);
   cudaMemcpy(c, clk_dev, sizeof(c), cudaMemcpyDeviceToHost);
-  fprintf(stderr, "systolic phase kclk/step [waitV u waitRow P2+P3 P4 P5+P6 P7 slide]: %.2f %.2f %.2f %.2f %.2f %.2f %.2f %.2f (steps %d)\n",
-          c[0] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[1] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[2] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB),
-          c[3] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[4] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[5] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB),
-          c[6] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), c[7] / 1e3 / (h->n - 1 - DWHMC_CHASE_PROF * TB), h->n - 1 - DWHMC_CHASE_PROF * TB);
+  const double st = 1e3 * (h->n - 1 - DWHMC_CHASE_PROF * TB);
+  fprintf(stderr, "systolic kclk/step between barrier releases (k > 0: VP | u | ROW | P2 | P3 | z | wc | row | y | CORNER | ysum | w | upd; k = 0: three fewer):");
+  double tot = 0;
+  for (int i = 0; i < 16; ++i) { fprintf(stderr, " %.2f", c[i] / st); tot += c[i] / st; }
+  fprintf(stderr, "  total %.2f\n", tot);
   return DWHMC_OK;
 #else
   return dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem);
