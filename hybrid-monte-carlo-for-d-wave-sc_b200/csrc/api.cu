@@ -182,6 +182,7 @@ int dwhmc_create(dwhmc_handle* out, int device, int B, int Lx, int Ly, const int
     const size_t nblk = h->band_blk_s0.size();
     AL(h->band_pos, (size_t)n); AL(h->band_prog, nB + (size_t)B); AL(h->band_tau, nB * h->band_KT);
     AL(h->band_rowbox, (size_t)B * h->band_KT * 2 * (h->band_b + 2));
+    AL(h->band_bbox, (size_t)B * h->band_KT * 2);
     AL(h->band_VT, (nblk * DW_APPLY_BLOCK_DOUBLES * B + 1) / 2);
     AL(h->band_blk_s0_dev, nblk); AL(h->band_blk_k_dev, nblk);
     {

@@ -1350,6 +1350,7 @@ int dw_band_chase(Handle* h, Mask mask) {
   const int n = h->n, B = h->B, bw = h->band_b;
   DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * ((size_t)n + 1) * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
+  DW_CUDA(h, cudaMemsetAsync(h->band_bbox, 0, sizeof(cplx) * 2 * (size_t)h->band_KT * B, h->stream));
   // DWHMC_BAND_GENERIC=1: the generic chase kernel (any half-bandwidth <= 101, load/store units instead of TMA) -- the
   // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;

@@ -121,6 +121,7 @@ __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;
 
 struct SysArgs {
   cplx* AB; cplx* V; cplx* tau2;
+  cplx* bbox;                    // [B][KT][2]: beta(s, k) and, 16 bytes on, the number of sweeps it is published for (one 32-byte sector)
   cplx* rowbox;                  // [B][KT][2][TB+2]: row message of (chain, position), slot = sweep & 1: row 0 of the updated Bc, then the corner of D
   int* flags;                    // [B][n]: vflag[k] at k, rflag[k] at KT + k, dflag[k] at 2 KT + k, sflag[k] (epochs saved) at 3 KT + k; then [1] task ticket
   int n, LD, KT, KP, B;          // KP: positions per chain
@@ -131,7 +132,7 @@ struct SysArgs {
 };
 
 // named barriers: 1 compute threads only; the others are shared with the helper warp (NC + 32 threads)
-enum { BAR_VP = 2, BAR_ROW = 3, BAR_CORNER = 4, BAR_VW = 5, BAR_RW = 6, BAR_DW = 7, BAR_TASK = 8, BAR_SAVE = 9 };
+enum { BAR_VP = 2, BAR_ROW = 3, BAR_CORNER = 4, BAR_VW = 5, BAR_RW = 6, BAR_DW = 7, BAR_TASK = 8, BAR_SAVE = 9, BAR_BETA = 10 };
 template <int NC> __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NC + 32) : "memory"); }
 template <int NC> __device__ __forceinline__ void hbar_arrive(int id) {
@@ -146,7 +147,7 @@ __host__ __device__ constexpr int sys_zrows(int tr) { return (tr % 2 == 0) ? tr 
 template <int TB, int TR, int TC>
 constexpr size_t sys_smem() {
   // D [TB][TB], partial sums [zrows + TC][TB+1], 10 vectors (vp x2, rowmsg x2, vs, xs, tu, wc, ys, xcol), red[32], 8 scalars, control
-  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 10 * TB + 2 + 32 + 10) + 64;
+  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 10 * TB + 2 + 32 + 11) + 64;
 }
 
 // One step of a position (sweep s), compute warps:
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   cplx* xcol = wc + TB;
   cplx* xrow = xcol + TB;                            // row 0 of Bc before the update (for the row message)
   cplx* red = xrow + TB;                             // [32]
-  cplx* scal = red + 32;                             // [10]: taup[2], -, -, tau, beta, -, -, poll buffer, mbarrier
-  volatile int* sw = reinterpret_cast<volatile int*>(scal + 10);   // [3] chain, position (-1: none left), epoch of the task just taken
+  cplx* scal = red + 32;                             // [11]: taup[2], -, -, tau, beta, beta of k+1 [2], poll buffer [2], mbarrier
+  volatile int* sw = reinterpret_cast<volatile int*>(scal + 11);   // [3] chain, position (-1: none left), epoch of the task just taken
   const int tid = threadIdx.x;
   const int n = g.n, LD = g.LD, KT = g.KT;
   const cplx zero = make_double2(0.0, 0.0);
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     const int lane = tid - NC;
     const bool l0 = lane == 0;
     bool dead = false;                               // a wait timed out: stop waiting, let the launch drain
-    unsigned long long* mb = reinterpret_cast<unsigned long long*>(scal + 9);   // completion barrier of the helper's bulk copies
-    cplx* pollbuf = scal + 8;                        // 16 bytes: the counters around the one being polled
+    unsigned long long* mb = reinterpret_cast<unsigned long long*>(scal + 10);  // completion barrier of the helper's bulk copies
+    cplx* pollbuf = scal + 8;                        // 32 bytes: the counters around the one being polled, or a beta slot
     unsigned ph = 0;
     if (l0) {
       mbar_init(mb, 1);
@@ -285,31 +286,57 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           __syncwarp();
         }
         hbar_arrive<NC>(BAR_VP);
-        // ... the row message of position k+1 (sweep s-1): row 0 of its updated Bc ...
+        // ... beta of step (s-1, k+1), the corner of the new last row of Bc: the one number of the neighbour's step
+        //     the reflector of this step depends on.  It travels in the 32-byte sector of its own counter, so the
+        //     poll that sees the counter has it already.
         cplx* rdst = rowbuf + buf * (TB + 1);
         const bool newrow = r0 + TB - 1 < n;         // the row / column that entered the windows exists
         const cplx* box_in = g.rowbox + (((size_t)chain * KT + (k + 1)) * 2 + ((s - 1) & 1)) * (TB + 2);
-        if (newrow) {
-          if (s > 0) {
-            wait_for(fl + KT + (k + 1), s);
-            if (l0) {
-              fence_async();
-              mbar_expect_tx(mb, (unsigned)(TB * sizeof(cplx)));
-              bulk_load(rdst, box_in, (unsigned)(TB * sizeof(cplx)), mb);
-              mbar_wait(mb, ph); ph ^= 1;
+        if (l0) {
+          cplx bt = zero;
+          if (newrow) {
+            if (s > 0) {
+              const cplx* slot = g.bbox + ((size_t)chain * KT + (k + 1)) * 2;
+              int spins = 0;
+              while (!dead) {
+                fence_async();
+                mbar_expect_tx(mb, 32);
+                bulk_load(pollbuf, slot, 32, mb);
+                mbar_wait(mb, ph); ph ^= 1;
+                if (reinterpret_cast<volatile int*>(pollbuf + 1)[0] >= s) break;
+                if (++spins > (1 << 20) || ((spins & 255) == 0 && *((volatile int*)g.status + 2) != 0)) {
+                  atomicExch(g.status + 2, 1);
+                  dead = true;
+                }
+              }
+              bt = pollbuf[0];
+            } else {
+              bt = ldg2(AB + (size_t)(r0 - 1) * LD + TB);   // first sweep: still in the band storage
             }
-            __syncwarp();
-          } else {                                   // first sweep: still in the band storage
-            for (int j = lane; j < TB; j += 32) rdst[j] = ldg2(AB + (size_t)(r0 - 1 + j) * LD + (TB - j));
-            if (l0) rdst[TB] = ldg2(AB + (size_t)(r0 + TB - 1) * LD);
           }
-        } else {
-          for (int j = lane; j <= TB; j += 32) rdst[j] = zero;
+          scal[6 + buf] = bt;
         }
-        hbar_arrive<NC>(BAR_ROW);
-        // ---- outputs of step s, and (when it is there) the corner of D(s-1, k+1), needed last
+        __syncwarp();
+        hbar_arrive<NC>(BAR_BETA);
+        // ---- v and beta of this step out
         hbar_sync<NC>(BAR_VW);
-        if (l0) st_release(fl + k, s + 1);             // (a release store is cumulative over what the barrier ordered)
+        if (l0) {
+          __threadfence();                             // (cumulative over what the barrier ordered)
+          asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(fl + k), "r"(s + 1) : "memory");
+          asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(reinterpret_cast<int*>(g.bbox + ((size_t)chain * KT + k) * 2 + 1)), "r"(s + 1) : "memory");
+        }
+        // ---- the rest of the neighbour's messages: row 0 of its updated Bc (the new last row of D), needed before
+        //      y = D v, and the corner of its D, needed after; one look at each before this step's own row message
+        //      goes out, so that a late neighbour does not hold it up
+        auto fetch_row = [&]() {
+          if (l0) {
+            fence_async();
+            mbar_expect_tx(mb, (unsigned)(TB * sizeof(cplx)));
+            bulk_load(rdst, box_in, (unsigned)(TB * sizeof(cplx)), mb);
+            mbar_wait(mb, ph); ph ^= 1;
+          }
+          __syncwarp();
+        };
         auto fetch_corner = [&]() {
           if (l0) {
             fence_async();
@@ -319,9 +346,23 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           }
           __syncwarp();
         };
-        const bool need_corner = newrow && s > 0;
-        bool have_corner = !need_corner;
-        if (need_corner) {                           // one look: do not hold up the row message of this step for it
+        bool have_row = false, have_corner = false;
+        if (newrow && s > 0) {
+          int ready = 0;
+          if (l0) ready = probe(fl + KT + (k + 1), s);
+          ready = __shfl_sync(0xffffffffu, ready, 0);
+          if (ready) { fetch_row(); have_row = true; }
+        } else {
+          if (newrow) {                               // first sweep: still in the band storage
+            for (int j = lane; j < TB; j += 32) rdst[j] = ldg2(AB + (size_t)(r0 - 1 + j) * LD + (TB - j));
+            if (l0) rdst[TB] = ldg2(AB + (size_t)(r0 + TB - 1) * LD);
+          } else {
+            for (int j = lane; j <= TB; j += 32) rdst[j] = zero;
+          }
+          have_row = have_corner = true;
+        }
+        if (have_row) hbar_arrive<NC>(BAR_ROW);
+        if (have_row && !have_corner) {
           int ready = 0;
           if (l0) ready = probe(fl + 2 * KT + (k + 1), s);
           ready = __shfl_sync(0xffffffffu, ready, 0);
@@ -330,6 +371,11 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if (have_corner) hbar_arrive<NC>(BAR_CORNER);
         hbar_sync<NC>(BAR_RW);
         if (l0) st_release(fl + KT + k, s + 1);
+        if (!have_row) {
+          wait_for(fl + KT + (k + 1), s);
+          fetch_row();
+          hbar_arrive<NC>(BAR_ROW);
+        }
         if (!have_corner) {
           wait_for(fl + 2 * KT + (k + 1), s);
           fetch_corner();
@@ -468,15 +514,16 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       csync<NC>();
       PH(1);
-      hbar_sync<NC>(BAR_ROW);
+      hbar_sync<NC>(BAR_BETA);
       PH(2);
-      // ---- P2: u, x and its norm; the row / column that entered D (its corner is added in P5)
+      // ---- P2: u, x and its norm (beta of the neighbour's step: the corner of the new last row of Bc)
       {
+        const cplx betain = scal[6 + buf];
         double nrm2 = 0.0;
         if (k > 0) {
           cplx u = sumL(party, ei, TC, ei < TB);
           if (esl == 0 && ei < TB) {
-            if (ei == po) cfma(u, rowm[0], vp[po]);
+            if (ei == po) cfma(u, betain, vp[po]);
             const cplx t = cmul(scal[buf], u);
             tu[ei] = t;
             const cplx x = csub(xcol[ei], t);
@@ -489,24 +536,14 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
               if (ri + q * TR == po) {
 #pragma unroll
                 for (int cc = 0; cc < CB; ++cc)
-                  if (cj + cc * TC == po) Bc[q][cc] = rowm[0];
+                  if (cj + cc * TC == po) Bc[q][cc] = betain;
               }
           }
         } else {
           for (int p = tid; p < TB; p += NC) {
-            const cplx x = (p == po) ? rowm[0] : xcol[p];
+            const cplx x = (p == po) ? betain : xcol[p];
             xs[p] = x;
             if (p != o) nrm2 += x.x * x.x + x.y * x.y;
-          }
-        }
-        for (int p = tid; p < TB; p += NC) {
-          if (p != po) {
-            const int j = p - po + (p < po ? TB : 0);
-            const cplx val = rowm[j];
-            D[p * LDD + po] = val;                      // row po, column p
-            D[po * LDD + p] = cconj(val);
-          } else {
-            D[po * LDD + po] = zero;
           }
         }
         nrm2 = warp_sum(make_double2(nrm2, 0.0)).x;
@@ -547,6 +584,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if (tid == 0) {
           stg2(g.tau2 + ((size_t)chain * n + s) * KT + k, lds2(scal + 4));
           if (k == 0) stg2(AB + (size_t)s * LD + 1, lds2(scal + 5));   // e[s]
+          else stg2(g.bbox + ((size_t)chain * KT + k) * 2, lds2(scal + 5));   // beta: position k-1 needs it before anything else
         }
       }
       hbar_arrive<NC>(BAR_VW);
@@ -602,6 +640,19 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
       }
       hbar_arrive<NC>(BAR_RW);
+      // ---- the row / column that entered D (the rest of the neighbour's row message; its corner is added in P5b)
+      hbar_sync<NC>(BAR_ROW);
+      for (int p = tid; p < TB; p += NC) {
+        if (p != po) {
+          const int j = p - po + (p < po ? TB : 0);
+          const cplx val = rowm[j];
+          D[p * LDD + po] = val;                        // row po, column p
+          D[po * LDD + p] = cconj(val);
+        } else {
+          D[po * LDD + po] = zero;
+        }
+      }
+      csync<NC>();
       // ---- P4b: y = D v (shared memory), partial sums
       if (act) {
         cplx acc[RB];
@@ -774,7 +825,7 @@ static int sys_dispatch(Handle* h, Mask mask) {
   DW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
   if (per_sm < 1) { h->err = "dw_band_chase_systolic: kernel does not fit"; return DWHMC_E_CUDA; }
   SysArgs a;
-  a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.flags = h->band_prog; a.rowbox = h->band_rowbox;
+  a.AB = h->A; a.V = h->V; a.tau2 = h->band_tau; a.flags = h->band_prog; a.rowbox = h->band_rowbox; a.bbox = h->band_bbox;
   a.n = h->n; a.LD = h->band_LD; a.KT = h->band_KT; a.KP = (h->n - 2) / TB + 1; a.B = h->B;
   a.status = h->status; a.mask = mask; a.clk = nullptr;
   // Epochs: with more position tasks than CTAs a chain is cut into epochs of Q sweeps, so that the CTAs the short

@@ -136,6 +136,7 @@ struct Handle {
   int* band_prog = nullptr;     // device [n*B]: steps completed per sweep (pipelining of the bulge chase); then [B]: next sweep to hand out
   cplx* band_tau = nullptr;     // device [n*KT*B]: tau of reflector (sweep, step)
   cplx* band_rowbox = nullptr;  // device [B][KT][2][b+2]: row messages of the position-owning chase (band_systolic.cu)
+  cplx* band_bbox = nullptr;    // device [B][KT][2]: beta of a step and, in the same 32-byte sector, the counter that publishes it
   cplx* band_VT = nullptr;      // device, DW_APPLY_BLOCK_DOUBLES doubles per (chain, block): conj(V) and -V T, operand planes of the back-transformation
   int band_nitems = 0;                    // work items per chain of the back-transformation (blocks x column parts, wavefront order)
   int band_apply_attr = 0;                // row tiles of the apply kernel instance whose shared-memory attribute is set
