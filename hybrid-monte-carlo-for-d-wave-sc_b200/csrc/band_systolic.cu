@@ -710,35 +710,55 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       hbar_arrive<NC>(BAR_DW);
       if (act) {
-        // column by column: the row operands (v, w, tu of this thread's RB rows) stay in registers, the column operands
-        // are broadcast loads; the register-only update of Bc covers the latency of the shared-memory update of D
-        cplx vq[RB], wq[RB], tq[RB];
+        // Two independent updates: Bc in registers (pure FP64 work; row operands v, tu held, column operands by broadcast
+        // loads) and D in shared memory (a read and a write per element: shared-memory bound).  Warps alternate in
+        // which one they do first, so that at any time half of them load the FP64 pipe and half the shared-memory
+        // pipe.  Inside a loop the operands of column c+1 are requested before the arithmetic of column c.
+        auto bc_update = [&]() {
+          if (k == 0) return;
+          cplx vq[RB], tq[RB];
 #pragma unroll
-        for (int q = 0; q < RB; ++q) { vq[q] = vs[ri + q * TR]; wq[q] = ys[ri + q * TR]; tq[q] = tu[ri + q * TR]; }
+          for (int q = 0; q < RB; ++q) { vq[q] = vs[ri + q * TR]; tq[q] = tu[ri + q * TR]; }
+          cplx cvpn = lds2(vp + cj), wjn = lds2(wc + cj);
 #pragma unroll
-        for (int cc = 0; cc < CB; ++cc) {
-          if (!JV(cc)) continue;
-          const int j = cj + cc * TC;
-          // every shared-memory operand of the column first, then the arithmetic: one load latency per column
-          cplx cvp = zero, wj = zero;
-          if (k > 0) { cvp = lds2(vp + j); wj = lds2(wc + j); }
-          cplx dq[RB];
-#pragma unroll
-          for (int q = 0; q < RB; ++q) dq[q] = lds2(D + j * LDD + ri + q * TR);
-          const cplx cwj = cconj(lds2(ys + j)), cvj = cconj(lds2(vs + j));
-          if (k > 0) {
-            cvp = cconj(cvp);
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const cplx cvp = cconj(cvpn), wj = wjn;
+            if (cc + 1 < CB && JV(cc + 1)) { cvpn = lds2(vp + cj + (cc + 1) * TC); wjn = lds2(wc + cj + (cc + 1) * TC); }
 #pragma unroll
             for (int q = 0; q < RB; ++q) { cfms(Bc[q][cc], tq[q], cvp); cfms(Bc[q][cc], vq[q], wj); }
           }
+        };
+        auto d_update = [&]() {
+          cplx vq[RB], wq[RB];
 #pragma unroll
-          for (int q = 0; q < RB; ++q) {
-            cfms(dq[q], vq[q], cwj);
-            cfms(dq[q], wq[q], cvj);
-            if (ri + q * TR == j) dq[q].y = 0.0;
-            D[j * LDD + ri + q * TR] = dq[q];
+          for (int q = 0; q < RB; ++q) { vq[q] = vs[ri + q * TR]; wq[q] = ys[ri + q * TR]; }
+          cplx dn[RB];
+#pragma unroll
+          for (int q = 0; q < RB; ++q) dn[q] = lds2(D + cj * LDD + ri + q * TR);
+#pragma unroll
+          for (int cc = 0; cc < CB; ++cc) {
+            if (!JV(cc)) continue;
+            const int j = cj + cc * TC;
+            cplx dq[RB];
+#pragma unroll
+            for (int q = 0; q < RB; ++q) dq[q] = dn[q];
+            const cplx cwj = cconj(lds2(ys + j)), cvj = cconj(lds2(vs + j));
+            if (cc + 1 < CB && JV(cc + 1)) {
+#pragma unroll
+              for (int q = 0; q < RB; ++q) dn[q] = lds2(D + (j + TC) * LDD + ri + q * TR);
+            }
+#pragma unroll
+            for (int q = 0; q < RB; ++q) {
+              cfms(dq[q], vq[q], cwj);
+              cfms(dq[q], wq[q], cvj);
+              if (ri + q * TR == j) dq[q].y = 0.0;
+              D[j * LDD + ri + q * TR] = dq[q];
+            }
           }
-        }
+        };
+        if ((tid >> 5) & 1) { bc_update(); d_update(); }
+        else { d_update(); bc_update(); }
       }
       csync<NC>();
       PH(12);
