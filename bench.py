@@ -302,10 +302,10 @@ def run_ours(args):
     flops_per_solve = B * (40.0 / 3.0) * n ** 3        # 40/3 n^3 per eigendecomposition
     eig_tflops = n_solves * flops_per_solve / (eig_ms * 1e-3) / 1e12
     bw = cb.band_halfwidth()
-    route = ("band (free dense->band stage: folded site order; bulge chase chase_tmah_kernel, D&C dc_*_kernel + DMMA dc_gemm2_kernel, "
+    route = ("band (free dense->band stage: folded site order; position-owning bulge chase chase_sys_kernel, D&C dc_*_kernel + DMMA dc_gemm2_kernel, "
              "register-resident DMMA block reflectors band_apply2_kernel)" if bw else
              "dense (hetrd: hemv_reg_kernel + DMMA zgemm her2k, D&C, DMMA back-transformation)")
-    stages = {("tridiagonalize (band route: bulge chase, chase_tmah_kernel)" if bw else
+    stages = {("tridiagonalize (band route: position-owning bulge chase, chase_sys_kernel)" if bw else
                "tridiagonalize (dense route: hemv_reg_kernel + column steps + DMMA her2k)"): tm["tridiagonalize_ms"],
               "tridiagonal D&C": tm["stedc_ms"],
               "back-transformation": tm["backtransform_ms"]}
@@ -352,12 +352,13 @@ def run_ours(args):
             pass
         dominant = {"kernel": dom_name, "stage_ms_per_batched_eigensolve": stages[dom_name] / n_solves,
                     "share_of_eigensolve": stages[dom_name] / eig_ms,
-                    "bound": ("latency (per-step dependency chain; neither FP64 pipe, shared memory, L2 nor HBM saturated)" if bw else
+                    "bound": ("latency (a chain of barrier-separated phases per step; shared-memory pipe ~50 %, FP64 pipe ~25 %, L2 / HBM idle: "
+                              "the blocks never leave the SM)" if bw else
                               "hbm (the trailing-matrix product A v of the one-stage reduction: 1 flop per byte)"),
                     "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                     "note": "DRAM bytes cannot be measured outside a profiler; see ncu_reference for the committed capture"}
-        if ncu_ref and bw and "chase" in ncu_ref:
-            c = ncu_ref["chase"]
+        if ncu_ref and bw and "chase_sys" in ncu_ref:
+            c = ncu_ref["chase_sys"]
             gbs = c["dram_bytes"] / (c["duration_ms"] * 1e-3) / 1e9
             dominant["ncu_reference"] = dict(c, file=NCU_REFERENCE, achieved_gbs=gbs, frac_of_hbm_peak=gbs / hbm_peak,
                                              source="committed ncu --set full capture of this kernel, NOT measured in this run")
