@@ -207,6 +207,19 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     __syncwarp();
     // wait until *flag >= need: the 16-byte chunk around the counter is fetched by the bulk-copy engine again and again
     // (a polling load in the load/store pipe would stall the shared-memory loads of the compute warps behind it)
+#ifdef DWHMC_CHASE_PROF
+    long long hw[6] = {0, 0, 0, 0, 0, 0};            // helper waits: v, beta, row, corner, epoch, whole tasks
+    int hkind = 0;
+#define HW_BEGIN(kind) long long hw_t0_ = clock64(); hkind = kind;
+#define HW_END() hw[hkind] += clock64() - hw_t0_;
+#define HW_TASK_BEGIN() const long long hw_task0 = clock64();
+#define HW_TASK_END() do { hw[5] += clock64() - hw_task0; if (l0) for (int i_ = 0; i_ < 6; ++i_) { atomicAdd((unsigned long long*)g.clk + 16 + i_, (unsigned long long)hw[i_]); hw[i_] = 0; } } while (0)
+#else
+#define HW_BEGIN(kind)
+#define HW_END()
+#define HW_TASK_BEGIN()
+#define HW_TASK_END() do { } while (0)
+#endif
     auto wait_for = [&](const int* flag, int need) {
       if (l0 && !dead) {
         const int* chunk = reinterpret_cast<const int*>(reinterpret_cast<unsigned long long>(flag) & ~15ull);
@@ -259,7 +272,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       ep = __shfl_sync(0xffffffffu, ep, 0);
       cplx* AB = g.AB + (size_t)chain * n * LD;
       int* fl = g.flags + (size_t)chain * n;
-      if (k >= 0 && ep > 0) wait_for(fl + 3 * KT + k, ep);   // the windows of this position as the previous epoch left them
+      HW_TASK_BEGIN()
+      if (k >= 0 && ep > 0) { HW_BEGIN(4) wait_for(fl + 3 * KT + k, ep); HW_END() }   // the windows of this position as the previous epoch left them
       hbar_arrive<NC>(BAR_TASK);
       if (k < 0) return;
       const int s0 = ep * g.Q, s1 = min((ep + 1) * g.Q, n - 1 - k * TB);
@@ -268,7 +282,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         const int buf = s & 1;
         // ---- inputs of step s: v and tau of position k-1 (the columns of Bc always exist) ...
         if (k > 0) {
-          wait_for(fl + (k - 1), s + 1);
+          { HW_BEGIN(0) wait_for(fl + (k - 1), s + 1); HW_END() }
           if (l0) {
             const cplx* Vseg = g.V + ((size_t)chain * n + s) * n + (r0 - TB);
             cplx* dst = vpbuf + buf * TB;
@@ -298,6 +312,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
             if (s > 0) {
               const cplx* slot = g.bbox + ((size_t)chain * KT + (k + 1)) * 2;
               int spins = 0;
+              HW_BEGIN(1)
               while (!dead) {
                 fence_async();
                 mbar_expect_tx(mb, 32);
@@ -309,6 +324,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
                   dead = true;
                 }
               }
+              HW_END()
               bt = pollbuf[0];
             } else {
               bt = ldg2(AB + (size_t)(r0 - 1) * LD + TB);   // first sweep: still in the band storage
@@ -372,12 +388,12 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         hbar_sync<NC>(BAR_RW);
         if (l0) st_release(fl + KT + k, s + 1);
         if (!have_row) {
-          wait_for(fl + KT + (k + 1), s);
+          { HW_BEGIN(2) wait_for(fl + KT + (k + 1), s); HW_END() }
           fetch_row();
           hbar_arrive<NC>(BAR_ROW);
         }
         if (!have_corner) {
-          wait_for(fl + 2 * KT + (k + 1), s);
+          { HW_BEGIN(3) wait_for(fl + 2 * KT + (k + 1), s); HW_END() }
           fetch_corner();
           hbar_arrive<NC>(BAR_CORNER);
         }
@@ -387,6 +403,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         o = (o + 1 == TB) ? 0 : o + 1;
       }
       hbar_sync<NC>(BAR_SAVE);                         // windows written back (if the position goes on in the next epoch)
+      HW_TASK_END();
       if (l0 && s1 < n - 1 - k * TB) st_release(fl + 3 * KT + k, ep + 1);
     }
   }
@@ -421,13 +438,20 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
 // release: the read is made to depend on a shared-memory load behind the barrier)
 #define PH(i) do { if (prof) { const int d_ = *reinterpret_cast<volatile int*>(sw); long long t_; \
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(d_) : "memory"); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+  long long cw[6] = {0, 0, 0, 0, 0, 0};            // time blocked at the helper's barriers: v, beta, row, corner, task; whole tasks
+#define CW_SYNC(id, slot) do { const long long c0_ = clock64(); hbar_sync<NC>(id); if (tid == 0) { const int d_ = *reinterpret_cast<volatile int*>(sw); long long t_; \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(d_) : "memory"); cw[slot] += t_ - c0_; } } while (0)
 #else
 #define PH(i) do { } while (0)
+#define CW_SYNC(id, slot) hbar_sync<NC>(id)
 #endif
   for (;;) {
-    hbar_sync<NC>(BAR_TASK);
+    CW_SYNC(BAR_TASK, 4);
     const int chain = sw[0], k = sw[1];
     if (k < 0) break;
+#ifdef DWHMC_CHASE_PROF
+    const long long ctask0 = clock64();
+#endif
 #ifdef DWHMC_CHASE_PROF
     if (prof) { for (int i = 0; i < 16; ++i) g.clk[i] = tph[i]; }
     prof = g.clk != nullptr && tid == 0 && chain == 0 && k == DWHMC_CHASE_PROF;
@@ -484,7 +508,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       const cplx* vp = vpbuf + buf * TB;
       const cplx* rowm = rowbuf + buf * (TB + 1);
       // ---- P1: u = Bc vp (the new last row of Bc is still zero; its corner comes with the row message)
-      hbar_sync<NC>(BAR_VP);
+      CW_SYNC(BAR_VP, 0);
       PH(0);
       if (k > 0 && act) {
         cplx acc[RB];
@@ -514,7 +538,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       csync<NC>();
       PH(1);
-      hbar_sync<NC>(BAR_BETA);
+      CW_SYNC(BAR_BETA, 1);
       PH(2);
       // ---- P2: u, x and its norm (beta of the neighbour's step: the corner of the new last row of Bc)
       {
@@ -641,7 +665,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       hbar_arrive<NC>(BAR_RW);
       // ---- the row / column that entered D (the rest of the neighbour's row message; its corner is added in P5b)
-      hbar_sync<NC>(BAR_ROW);
+      CW_SYNC(BAR_ROW, 2);
       for (int p = tid; p < TB; p += NC) {
         if (p != po) {
           const int j = p - po + (p < po ? TB : 0);
@@ -671,7 +695,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
       csync<NC>();
       PH(8);
-      hbar_sync<NC>(BAR_CORNER);
+      CW_SYNC(BAR_CORNER, 3);
       PH(9);
       // ---- P5b: y = tau D v (with the corner that entered), y^H v
       {
@@ -818,6 +842,9 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       }
     }
     hbar_arrive<NC>(BAR_SAVE);
+#ifdef DWHMC_CHASE_PROF
+    if (tid == 0 && g.clk) { cw[5] = clock64() - ctask0; for (int i_ = 0; i_ < 6; ++i_) { atomicAdd((unsigned long long*)g.clk + 24 + i_, (unsigned long long)cw[i_]); cw[i_] = 0; } }
+#endif
   }
 #ifdef DWHMC_CHASE_PROF
   if (prof) { for (int i = 0; i < 16; ++i) g.clk[i] = tph[i]; }
@@ -858,7 +885,8 @@ static int sys_dispatch(Handle* h, Mask mask) {
   void* args[] = {&a};
 #ifdef DWHMC_CHASE_PROF                                  // phase clocks of position DWHMC_CHASE_PROF of chain 0 (experiments)
   static long long* clk_dev = nullptr;
-  if (!clk_dev) { cudaMalloc(&clk_dev, 16 * sizeof(long long)); cudaMemset(clk_dev, 0, 16 * sizeof(long long)); }
+  if (!clk_dev) { cudaMalloc(&clk_dev, 32 * sizeof(long long)); }
+  cudaMemsetAsync(clk_dev, 0, 32 * sizeof(long long), h->stream);
   a.clk = clk_dev;
   DW_TRY(dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem));
   long long c[16];
@@ -869,6 +897,14 @@ static int sys_dispatch(Handle* h, Mask mask) {
   double tot = 0;
   for (int i = 0; i < 16; ++i) { fprintf(stderr, " %.2f", c[i] / st); tot += c[i] / st; }
   fprintf(stderr, "  total %.2f\n", tot);
+  long long hwv[6];
+  cudaMemcpy(hwv, clk_dev + 16, sizeof(hwv), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "helper waits, share of all task time: v %.3f beta %.3f row %.3f corner %.3f epoch %.3f (tasks: %.1f Mclk on %d CTAs)\n",
+          (double)hwv[0] / hwv[5], (double)hwv[1] / hwv[5], (double)hwv[2] / hwv[5], (double)hwv[3] / hwv[5], (double)hwv[4] / hwv[5],
+          hwv[5] / 1e6, nctas);
+  cudaMemcpy(hwv, clk_dev + 24, sizeof(hwv), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "compute warps blocked at the helper's barriers, share of all task time: v %.3f beta %.3f row %.3f corner %.3f next task %.3f\n",
+          (double)hwv[0] / hwv[5], (double)hwv[1] / hwv[5], (double)hwv[2] / hwv[5], (double)hwv[3] / hwv[5], (double)hwv[4] / hwv[5]);
   return DWHMC_OK;
 #else
   return dw_chase_launch_guarded(h, kern, nctas, nthreads, args, smem);
