@@ -80,7 +80,7 @@ struct StageTimer {
 
 extern "C" {
 
-const char* dwhmc_version(void) { return "dwhmc-b200 0.2 (sm_100a; FP64 DMMA m8n8k4; band route: TMA bulge chase + D&C + fused block reflectors; dense route: hetrd + D&C + blocked back-transform)"; }
+const char* dwhmc_version(void) { return "dwhmc-b200 0.3 (sm_100a; FP64 DMMA m8n8k4; band route: position-owning bulge chase + D&C + fused block reflectors; dense route: hetrd + D&C + blocked back-transform)"; }
 
 const char* dwhmc_last_error(dwhmc_handle hh) {
   if (!hh) return g_create_err.c_str();
