@@ -1355,16 +1355,12 @@ int dw_band_chase(Handle* h, Mask mask) {
   // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
   static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
   // Default wherever it has an instance: the position-owning kernel of band_systolic.cu (one chain finishes in n step
-  // times instead of 2 n, and the blocks never leave the SM: 10.9 instead of 30.5 ms for up to 12 chains at L = 24,
-  // 33.2 instead of 46 ms for 64; L = 20: 7.6 / 18.7 / 36 ms for 16 / 64 / 128 chains against 15.2 / 18.6 / 74).  The
-  // sweep-owning TMA kernel below keeps one window where it is ahead by 10-20 %: small half-bandwidths (short steps,
-  // where the fixed cost of a position's step counts) with about two CTAs per chain (L = 16: 64 chains 8.3 against
-  // 9.4 ms, L = 12: 3.4 against 4.2).  DWHMC_CHASE=sweep | systolic forces one of the two.
+  // times instead of 2 n, and the blocks never leave the SM): at L = 24 10.0 instead of 30.5 ms for up to 12 chains and
+  // 30.2 instead of 46 ms for 64; L = 20: 15.8 against 18.6 ms for 64 chains, L = 16: 7.0 against 8.3.
+  // DWHMC_CHASE=sweep forces the sweep-owning TMA kernel below, the band route's second kernel.
   static const char* which = getenv("DWHMC_CHASE");
   bool use_sys = dw_band_has_systolic_kernel(bw);
-  if (use_sys && bw <= 68 && 2 * B <= h->nsm && 2LL * B * ((n - 2) / bw + 1) > 5LL * h->nsm && dw_band_has_tma_kernel(bw)) use_sys = false;
   if (which && which[0] == 's' && which[1] == 'w') use_sys = false;
-  if (which && which[0] == 's' && which[1] == 'y') use_sys = dw_band_has_systolic_kernel(bw);
   if (!generic && use_sys) DW_TRY(dw_band_chase_systolic(h, mask));
   else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
   else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));

@@ -18,9 +18,9 @@
 //     guarded by three release / acquire counters per (chain, position): vflag, bflag, dflag = sweeps published.
 //     The column that leaves D on a slide becomes the new last column of Bc (position 0: the next column to
 //     annihilate).  Position 0 also delivers the tridiagonal matrix (d, e) into AB where band_de_kernel reads it.
-//   * a helper warp does everything that waits on the memory system: it polls the neighbours' counters, brings
-//     their messages into (double-buffered) shared memory ahead of time and publishes this position's counters;
-//     the compute warps meet it at named barriers only.
+//   * a helper warp does everything that waits on the memory system: it polls the neighbours' counters (acquire
+//     loads), brings their messages into (double-buffered) shared memory ahead of time (L2 loads) and publishes this
+//     position's counters (release stores); the compute warps meet it at named barriers only.
 // Global traffic per step drops from 3 b^2 elements (two tensor copies and the diagonal block through L2) to ~4 b.
 // Tasks (chain, position) are handed out by one ticket counter in (chain, position) order: whoever waits for a
 // neighbour waits for a task with a smaller ticket or for the next untaken ones, which the CTAs of finished
@@ -76,13 +76,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// spin with relaxed loads (an acquire load invalidates the SM's L1 on every poll), one fence after success
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -96,28 +89,6 @@ __device__ __forceinline__ cplx lds2(const cplx* p) {
   asm LDS2_VOLATILE("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
   return v;
 }
-
-// bulk-copy engine (TMA): the helper warp brings the neighbours' messages in with it, so no global load of the
-// helper sits in the load/store pipe the compute warps read shared memory through
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok = 0;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct SysArgs {
   cplx* AB; cplx* V; cplx* tau2;
@@ -185,7 +156,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   cplx* xcol = wc + TB;
   cplx* xrow = xcol + TB;                            // row 0 of Bc before the update (for the row message)
   cplx* red = xrow + TB;                             // [32]
-  cplx* scal = red + 32;                             // [11]: taup[2], -, -, tau, beta, beta of k+1 [2], poll buffer [2], mbarrier
+  cplx* scal = red + 32;                             // [11]: taup[2], -, -, tau, beta, beta of k+1 [2]
   volatile int* sw = reinterpret_cast<volatile int*>(scal + 11);   // [3] chain, position (-1: none left), epoch of the task just taken
   const int tid = threadIdx.x;
   const int n = g.n, LD = g.LD, KT = g.KT;
@@ -197,16 +168,6 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
     const int lane = tid - NC;
     const bool l0 = lane == 0;
     bool dead = false;                               // a wait timed out: stop waiting, let the launch drain
-    unsigned long long* mb = reinterpret_cast<unsigned long long*>(scal + 10);  // completion barrier of the helper's bulk copies
-    cplx* pollbuf = scal + 8;                        // 32 bytes: the counters around the one being polled, or a beta slot
-    unsigned ph = 0;
-    if (l0) {
-      mbar_init(mb, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    // wait until *flag >= need: the 16-byte chunk around the counter is fetched by the bulk-copy engine again and again
-    // (a polling load in the load/store pipe would stall the shared-memory loads of the compute warps behind it)
 #ifdef DWHMC_CHASE_PROF
     long long hw[6] = {0, 0, 0, 0, 0, 0};            // helper waits: v, beta, row, corner, epoch, whole tasks
     int hkind = 0;
@@ -220,18 +181,12 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
 #define HW_TASK_BEGIN()
 #define HW_TASK_END() do { } while (0)
 #endif
+    // wait until *flag >= need (acquire loads by lane 0; the payload is then read by the whole warp with L2 loads)
     auto wait_for = [&](const int* flag, int need) {
       if (l0 && !dead) {
-        const int* chunk = reinterpret_cast<const int*>(reinterpret_cast<unsigned long long>(flag) & ~15ull);
-        const int off = (int)(flag - chunk);
         int spins = 0;
-        for (;;) {
-          fence_async();
-          mbar_expect_tx(mb, 16);
-          bulk_load(pollbuf, chunk, 16, mb);
-          mbar_wait(mb, ph); ph ^= 1;
-          if (reinterpret_cast<volatile int*>(pollbuf)[off] >= need) break;
-          if (++spins > (1 << 20) || ((spins & 255) == 0 && *((volatile int*)g.status + 2) != 0)) {
+        while (ld_acquire(flag) < need) {
+          if (++spins > (1 << 22) || ((spins & 1023) == 0 && *((volatile int*)g.status + 2) != 0)) {
             atomicExch(g.status + 2, 1);
             dead = true;
             break;
@@ -239,14 +194,6 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
       }
       __syncwarp();
-    };
-    auto probe = [&](const int* flag, int need) -> int {   // lane 0: one look at a counter
-      const int* chunk = reinterpret_cast<const int*>(reinterpret_cast<unsigned long long>(flag) & ~15ull);
-      fence_async();
-      mbar_expect_tx(mb, 16);
-      bulk_load(pollbuf, chunk, 16, mb);
-      mbar_wait(mb, ph); ph ^= 1;
-      return reinterpret_cast<volatile int*>(pollbuf)[(int)(flag - chunk)] >= need ? 1 : 0;
     };
     for (;;) {
       int chain = 0, k = -1, ep = 0;
@@ -283,21 +230,11 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         // ---- inputs of step s: v and tau of position k-1 (the columns of Bc always exist) ...
         if (k > 0) {
           { HW_BEGIN(0) wait_for(fl + (k - 1), s + 1); HW_END() }
-          if (l0) {
+          {
             const cplx* Vseg = g.V + ((size_t)chain * n + s) * n + (r0 - TB);
-            cplx* dst = vpbuf + buf * TB;
-            fence_async();
-            mbar_expect_tx(mb, (unsigned)((TB + 1) * sizeof(cplx)));
-            if (o > 0) {                             // logical index l -> physical (o + l) mod TB: two pieces
-              bulk_load(dst + o, Vseg, (unsigned)((TB - o) * sizeof(cplx)), mb);
-              bulk_load(dst, Vseg + (TB - o), (unsigned)(o * sizeof(cplx)), mb);
-            } else {
-              bulk_load(dst, Vseg, (unsigned)(TB * sizeof(cplx)), mb);
-            }
-            bulk_load(scal + buf, g.tau2 + ((size_t)chain * n + s) * KT + (k - 1), (unsigned)sizeof(cplx), mb);
-            mbar_wait(mb, ph); ph ^= 1;
+            for (int p = lane; p < TB; p += 32) vpbuf[buf * TB + p] = ldg2(Vseg + (p - o + (p < o ? TB : 0)));
+            if (l0) scal[buf] = ldg2(g.tau2 + ((size_t)chain * n + s) * KT + (k - 1));
           }
-          __syncwarp();
         }
         hbar_arrive<NC>(BAR_VP);
         // ... beta of step (s-1, k+1), the corner of the new last row of Bc: the one number of the neighbour's step
@@ -313,19 +250,15 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
               const cplx* slot = g.bbox + ((size_t)chain * KT + (k + 1)) * 2;
               int spins = 0;
               HW_BEGIN(1)
-              while (!dead) {
-                fence_async();
-                mbar_expect_tx(mb, 32);
-                bulk_load(pollbuf, slot, 32, mb);
-                mbar_wait(mb, ph); ph ^= 1;
-                if (reinterpret_cast<volatile int*>(pollbuf + 1)[0] >= s) break;
-                if (++spins > (1 << 20) || ((spins & 255) == 0 && *((volatile int*)g.status + 2) != 0)) {
+              const int* bflag = reinterpret_cast<const int*>(slot + 1);
+              while (!dead && ld_acquire(bflag) < s) {
+                if (++spins > (1 << 22) || ((spins & 1023) == 0 && *((volatile int*)g.status + 2) != 0)) {
                   atomicExch(g.status + 2, 1);
                   dead = true;
                 }
               }
               HW_END()
-              bt = pollbuf[0];
+              bt = ldg2(slot);
             } else {
               bt = ldg2(AB + (size_t)(r0 - 1) * LD + TB);   // first sweep: still in the band storage
             }
@@ -345,27 +278,17 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         //      y = D v, and the corner of its D, needed after; one look at each before this step's own row message
         //      goes out, so that a late neighbour does not hold it up
         auto fetch_row = [&]() {
-          if (l0) {
-            fence_async();
-            mbar_expect_tx(mb, (unsigned)(TB * sizeof(cplx)));
-            bulk_load(rdst, box_in, (unsigned)(TB * sizeof(cplx)), mb);
-            mbar_wait(mb, ph); ph ^= 1;
-          }
+          for (int j = lane; j < TB; j += 32) rdst[j] = ldg2(box_in + j);
           __syncwarp();
         };
         auto fetch_corner = [&]() {
-          if (l0) {
-            fence_async();
-            mbar_expect_tx(mb, (unsigned)sizeof(cplx));
-            bulk_load(rdst + TB, box_in + TB, (unsigned)sizeof(cplx), mb);
-            mbar_wait(mb, ph); ph ^= 1;
-          }
+          if (l0) rdst[TB] = ldg2(box_in + TB);
           __syncwarp();
         };
         bool have_row = false, have_corner = false;
         if (newrow && s > 0) {
           int ready = 0;
-          if (l0) ready = probe(fl + KT + (k + 1), s);
+          if (l0) ready = ld_acquire(fl + KT + (k + 1)) >= s;
           ready = __shfl_sync(0xffffffffu, ready, 0);
           if (ready) { fetch_row(); have_row = true; }
         } else {
@@ -380,7 +303,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         if (have_row) hbar_arrive<NC>(BAR_ROW);
         if (have_row && !have_corner) {
           int ready = 0;
-          if (l0) ready = probe(fl + 2 * KT + (k + 1), s);
+          if (l0) ready = ld_acquire(fl + 2 * KT + (k + 1)) >= s;
           ready = __shfl_sync(0xffffffffu, ready, 0);
           if (ready) { fetch_corner(); have_corner = true; }
         }

@@ -760,9 +760,7 @@ CHASE_SWITCH_SHAPES = {
     "DWHMC_CHASE_Q=16": (["8", "150"], ["24", "3"], ["5x13", "2"]),
     "DWHMC_CHASE_Q=37": (["16", "40"], ["6x10", "3"]),
     # the sweep-owning kernel (band.cu), the band route's second kernel
-    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"], ["8", "150"]),
-    # the position-owning kernel in the one window where the sweep-owning one is the default
-    "DWHMC_CHASE=systolic": (["16", "64"], ["12", "64"]),
+    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"], ["8", "150"], ["16", "64"]),
 }
 
 
