@@ -379,8 +379,8 @@ def run_ours(args):
                                     "unchanged reference scripts (scripts/test_simulation.jl:25-31)",
                              "cpu_1_process_all_threads": cpu_modes.get("as_shipped_1proc_all_threads"),
                              "note": "one chain cannot fill the GPU: small batches run the position-owning bulge chase "
-                                     "(band_systolic.cu, 12 CTAs per chain at L = 24, one sweep per step time: ~15 ms per "
-                                     "eigensolve instead of ~31 with the sweep-owning kernel); batch chains (ChainBatch) for "
+                                     "(band_systolic.cu, 12 CTAs per chain at L = 24, one sweep per step time: ~10 ms per "
+                                     "chase instead of ~31 with the sweep-owning kernel); batch chains (ChainBatch) for "
                                      "throughput"},
             "gpu_launches": launches,
             "clocks": clk.summary(),

@@ -11,20 +11,25 @@
 //   * Bc lives in registers (RB x CB elements per thread, compile-time indices), D in shared memory with both
 //     triangles (a torus has no fixed lower triangle), rows / columns beyond the matrix are kept at zero, so the
 //     block operations carry no length masks.
-//   * per sweep a position exchanges O(b) numbers with its neighbours through their true places in global memory:
+//   * per sweep a position exchanges O(b) numbers with its neighbours through global memory:
 //       k-1 -> k   the reflector v(s, k-1) and tau (the V / tau outputs the back-transformation needs anyway)
-//       k+1 -> k   row 0 of Bc(s-1, k+1) after its update (new last row of D(s, k) and the corner of Bc(s, k)) and
-//                  the corner D(s-1, k+1)[0, 0], both written to the band storage AB
-//     guarded by three release / acquire counters per (chain, position): vflag, bflag, dflag = sweeps published.
+//       k+1 -> k   beta(s-1, k+1), the corner of the new last row of Bc(s, k) -- the one number the next reflector of
+//                  position k depends on: published right after the reflector, in the 32-byte sector of its own counter;
+//                  row 0 of Bc(s-1, k+1) after its update (the new last row of D(s, k)), formed right after z = v^H Bc
+//                  and needed before y = D v; the corner D(s-1, k+1)[0, 0], last.  Row and corner go to a mailbox of
+//                  two slots (sweep parity) per (chain, position).
+//     guarded by release / acquire counters per (chain, position): sweeps published for v + beta, row, corner.
 //     The column that leaves D on a slide becomes the new last column of Bc (position 0: the next column to
 //     annihilate).  Position 0 also delivers the tridiagonal matrix (d, e) into AB where band_de_kernel reads it.
 //   * a helper warp does everything that waits on the memory system: it polls the neighbours' counters (acquire
 //     loads), brings their messages into (double-buffered) shared memory ahead of time (L2 loads) and publishes this
 //     position's counters (release stores); the compute warps meet it at named barriers only.
 // Global traffic per step drops from 3 b^2 elements (two tensor copies and the diagonal block through L2) to ~4 b.
-// Tasks (chain, position) are handed out by one ticket counter in (chain, position) order: whoever waits for a
-// neighbour waits for a task with a smaller ticket or for the next untaken ones, which the CTAs of finished
-// positions pick up, so the cooperative launch cannot deadlock.
+// Tasks (epoch, chain, position) are handed out by one ticket counter in that order: after Q sweeps a position writes
+// its windows back to the band storage and whichever CTA is free continues it (so the CTAs the short positions of
+// early chains set free go to later chains at once and all chains end together).  Whoever waits for a neighbour waits
+// for a task with a smaller ticket or for the next untaken ones, which the CTAs of finished tasks pick up, so the
+// cooperative launch cannot deadlock.
 // NumPy prototype of exactly this organisation: tests/algo_proto_systolic.py (checked against the sweep-owning
 // prototype and LAPACK in tests/test_algo_proto.py).
 #include <cuda.h>
