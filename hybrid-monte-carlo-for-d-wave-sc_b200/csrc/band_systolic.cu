@@ -123,7 +123,7 @@ __host__ __device__ constexpr int sys_zrows(int tr) { return (tr % 2 == 0) ? tr 
 template <int TB, int TR, int TC>
 constexpr size_t sys_smem() {
   // D [TB][TB], partial sums [zrows + TC][TB+1], 10 vectors (vp x2, rowmsg x2, vs, xs, tu, wc, ys, xcol), red[32], 8 scalars, control
-  return sizeof(cplx) * ((size_t)TB * TB + (size_t)(sys_zrows(TR) + TC) * (TB + 1) + 10 * TB + 2 + 32 + 11) + 64;
+  return sizeof(cplx) * ((size_t)TB * TB + (size_t)sys_zrows(TR) * (TB + 1) + (size_t)TC * (TB + 8) + 10 * TB + 2 + 32 + 11) + 64;
 }
 
 // One step of a position (sweep s), compute warps:
@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   constexpr bool ZPAIR = TR % 2 == 0;
   constexpr int ZR = sys_zrows(TR);
   constexpr int LDD = TB;
-  constexpr int LDP = TB + 1;    // partial sums: odd leading dimension
+  constexpr int LDP = TB + 1;    // partial sums of z: odd leading dimension (its rows are written by every second lane)
+  // partial sums of u and y: read back by LPE lanes per entry, row q = esl + LPE i -- conflict-free when LPE LDY = 8 mod 16
+  constexpr int LDY = (LPE == 1) ? TB + 1 : TB + ((8 / LPE - TB % 8) + 8) % 8;
   extern __shared__ __align__(16) unsigned char smem_sys[];
   cplx* D = reinterpret_cast<cplx*>(smem_sys);       // [TB][LDD] physical column-major, both triangles
   cplx* partz = D + TB * LDD;                        // [ZR][LDP] partial sums of z (column TB: v^H tu)
-  cplx* party = partz + ZR * LDP;                    // [TC][LDP] partial sums of u, then of y
-  cplx* vpbuf = party + TC * LDP;                    // [2][TB] previous reflector (physical column index)
+  cplx* party = partz + ZR * LDP;                    // [TC][LDY] partial sums of u, then of y
+  cplx* vpbuf = party + TC * LDY;                    // [2][TB] previous reflector (physical column index)
   cplx* rowbuf = vpbuf + 2 * TB;                     // [2][TB+1] row message of position k+1: row, corner
   cplx* vs = rowbuf + 2 * (TB + 1);
   cplx* xs = vs + TB;
@@ -340,10 +342,10 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
   const bool act = tid < TR * TC;
   const int ri = act ? tid % TR : 0, cj = act ? tid / TR : 0;
   const int ei = tid / LPE, esl = tid % LPE;         // LPE lanes per entry of a matrix-vector product
-  auto sumL = [&](const cplx* part, int col, int nq, bool valid) -> cplx {   // sum_q part[q][col], q < nq; result in all LPE lanes
+  auto sumL = [&](const cplx* part, int ld, int col, int nq, bool valid) -> cplx {   // sum_q part[q][col], q < nq; result in all LPE lanes
     cplx a = zero;
     if (valid)
-      for (int q = esl; q < nq; q += LPE) a = cadd(a, part[q * LDP + col]);
+      for (int q = esl; q < nq; q += LPE) a = cadd(a, part[q * ld + col]);
     if (LPE >= 2) { a.x += __shfl_xor_sync(0xffffffffu, a.x, 1); a.y += __shfl_xor_sync(0xffffffffu, a.y, 1); }
     if (LPE >= 4) { a.x += __shfl_xor_sync(0xffffffffu, a.x, 2); a.y += __shfl_xor_sync(0xffffffffu, a.y, 2); }
     return a;
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           }
         }
 #pragma unroll
-        for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+        for (int q = 0; q < RB; ++q) party[cj * LDY + ri + q * TR] = acc[q];
 #pragma unroll
         for (int q = 0; q < RB; ++q)
           if (ri + q * TR == o) {                     // logical row 0 as it is now: the row message is formed from it in P5a
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         const cplx betain = scal[6 + buf];
         double nrm2 = 0.0;
         if (k > 0) {
-          cplx u = sumL(party, ei, TC, ei < TB);
+          cplx u = sumL(party, LDY, ei, TC, ei < TB);
           if (esl == 0 && ei < TB) {
             if (ei == po) cfma(u, betain, vp[po]);
             const cplx t = cmul(scal[buf], u);
@@ -575,8 +577,8 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         {
           // wc = conj(tau) z, and with it row r0 of the updated Bc -- the row message -- straight to its mailbox:
           // Bc[0, j] - tu[0] conj(vp[j]) - v[0] wc[j] with v[0] = 1; the annihilated column holds beta
-          cplx z = sumL(partz, ei, ZR, ei < TB);
-          const cplx c = sumL(partz, TB, ZR, true);
+          cplx z = sumL(partz, LDP, ei, ZR, ei < TB);
+          const cplx c = sumL(partz, LDP, TB, ZR, true);
           if (esl == 0 && ei < TB) {
             const cplx cvp = cconj(vp[ei]);
             cfms(z, c, cvp);
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           for (int q = 0; q < RB; ++q) cfma(acc[q], D[pc * LDD + ri + q * TR], vj);
         }
 #pragma unroll
-        for (int q = 0; q < RB; ++q) party[cj * LDP + ri + q * TR] = acc[q];
+        for (int q = 0; q < RB; ++q) party[cj * LDY + ri + q * TR] = acc[q];
       }
       csync<NC>();
       PH(8);
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       // ---- P5b: y = tau D v (with the corner that entered), y^H v
       {
         cplx dot = zero;
-        cplx y = sumL(party, ei, TC, ei < TB);
+        cplx y = sumL(party, LDY, ei, TC, ei < TB);
         if (esl == 0 && ei < TB) {
           if (ei == po) {
             const double corner = rowm[TB].x;
