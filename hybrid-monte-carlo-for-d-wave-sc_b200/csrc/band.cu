@@ -8,13 +8,13 @@
 //   chase           band -> real tridiagonal by Householder bulge chasing (Lang's algorithm):
 //                   sweep s, step k: reflector on rows s+1+kb .. s+(k+1)b; persistent CTAs, one sweep
 //                   each at a time, sweeps of a chain pipelined through release/acquire progress
-//                   counters (two steps apart in the TMA kernel, three in the generic chase_kernel);
+//                   counters (two steps apart);
 //                   the block pushed out by a step stays in shared memory for the next one (3 b^2
 //                   elements of global traffic per step).  chase_tmah_kernel<b, ...> (compile-time b,
 //                   the default): TMA tensor copies in column pieces, a helper warp for everything that
 //                   waits on the memory system, sweeps handed out by ticket counters to one CTA per SM,
-//                   the last b sweeps in chase_tail_kernel; chase_kernel (any b <= 101, load/store units)
-//                   is the one fallback (DWHMC_BAND_GENERIC=1).
+//                   the last b sweeps in chase_tail_kernel.  This sweep-owning kernel is the band route's
+//                   fallback (DWHMC_CHASE=sweep); the default is the position-owning kernel of band_systolic.cu.
 // The back-transformation U = Q2 Z (T factors, block reflectors on the FP64 tensor cores, rows back to the
 // reference's site order) is in band_apply.cu.
 // The numerics (LAPACK-style zlarfg / zhetd2 updates, application order of the blocks) are the
@@ -39,7 +39,6 @@ namespace {
 
 constexpr int CT = 512;             // threads per CTA of the chase kernel
 constexpr int CW = CT / 32;         // warps
-constexpr int RQ = 5;               // row chunks of 32 per lane: b <= 160
 
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -83,11 +82,6 @@ __device__ __forceinline__ cplx ldg2(const cplx* p) {
 }
 __device__ __forceinline__ void stg2(cplx* p, cplx v) {
   asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -152,310 +146,8 @@ struct ChaseArgs {
   long long* clk;                // optional [8] phase clock accumulators of CTA 0 (profiling experiments)
 };
 
-// LAPACK zlarfg on x (shared, length ln >= 1): v = x scaled, v[0] = 1 (left in vs); returns tau, beta.
-// Every thread gets the same (tau, beta).
-__device__ __forceinline__ void larfg_block(const cplx* xs, cplx* vs, int ln, cplx* red, cplx& tau, double& beta) {
-  const int tid = threadIdx.x;
-  cplx nrm = make_double2(0.0, 0.0);
-  for (int i = 1 + tid; i < ln; i += CT) { const cplx a = xs[i]; nrm.x += a.x * a.x + a.y * a.y; }
-  nrm = block_sum(nrm, red);
-  const cplx alpha = xs[0];
-  cplx scale;
-  if (nrm.x == 0.0 && alpha.y == 0.0) {
-    beta = alpha.x;
-    tau = make_double2(0.0, 0.0);
-    scale = make_double2(0.0, 0.0);
-  } else {
-    beta = -copysign(sqrt(alpha.x * alpha.x + alpha.y * alpha.y + nrm.x), alpha.x);
-    tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-    const double dr = alpha.x - beta, di = alpha.y, den = dr * dr + di * di;
-    scale = make_double2(dr / den, -di / den);
-  }
-  for (int i = tid; i < ln; i += CT) vs[i] = (i == 0) ? make_double2(1.0, 0.0) : cmul(xs[i], scale);
-  __syncthreads();
-}
-
-constexpr int EU = 20;              // elements of the b x b block per thread (b <= 101 at 512 threads)
-constexpr int DU = 10;              // elements of the folded lower triangle per thread
-
-// smem words of the chase kernel for half-bandwidth b (host and device must agree)
-__host__ __device__ inline size_t chase_smem_elems(int b) {
-  const int ldb = b | 1;
-  return (size_t)ldb * b + 6 * (size_t)b + 4 * (size_t)(32 * RQ) + 32;
-}
-
-// Folded enumeration of the lower triangle of an ln x ln block: columns c and ln-1-c together have
-// ln+1 entries.  slot -> (i, j); returns false for padding slots.
-__device__ __forceinline__ bool tri_slot(int slot, int ln, int& i, int& j) {
-  const int h = ln + 1;
-  const int c = slot / h, r = slot - c * h;
-  const int half = (ln + 1) >> 1;
-  if (c >= half) return false;
-  if (r < ln - c) { j = c; i = c + r; return true; }
-  if (2 * c + 1 == ln) return false;                 // middle column of an odd block has no partner
-  j = ln - 1 - c;
-  i = j + (r - (ln - c));
-  return true;
-}
-
-__global__ void __launch_bounds__(CT, 1) chase_kernel(ChaseArgs g) {
-  const int chain = g.c0 + blockIdx.x / g.P, p = blockIdx.x % g.P;
-  if (!g.mask.on(chain)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = g.n, b = g.b, LD = g.LD;
-  const int ldb = b | 1;                             // odd leading dimension: rows and columns both conflict-free
-  cplx* Bc = reinterpret_cast<cplx*>(smem_raw);      // [b][ldb] carried block / diagonal block, column-major
-  cplx* vs = Bc + (size_t)ldb * b;                   // current reflector
-  cplx* vp = vs + b;                                 // previous reflector (deferred right-application)
-  cplx* us = vp + b;                                 // Bc_raw vp
-  cplx* xs = us + b;                                 // column to annihilate / w
-  cplx* tu = xs + b;                                 // taup * us
-  cplx* wc = tu + b;                                 // conj(tau) z
-  cplx* part = wc + b;                               // [4][32 RQ] partial sums of the matrix-vector products
-  cplx* red = part + 4 * (32 * RQ);                  // [32]
-  const int tid = threadIdx.x;
-  cplx* AB = g.AB + (size_t)chain * n * LD;
-  cplx* V = g.V + (size_t)chain * n * n;
-  cplx* tau2 = g.tau2 + (size_t)chain * n * g.KT;
-  int* prog = g.prog + (size_t)chain * n;
-  const cplx zero = make_double2(0.0, 0.0);
-  // matrix-vector products from shared memory: thread = (row or column, part of the other index range)
-  const int rpad = (b + 31) & ~31;
-  const int nparts = min(4, CT / rpad);
-  const int mv_row = tid % rpad, mv_part = tid / rpad;
-  const int PS = 32 * RQ;
-
-#ifdef DWHMC_CHASE_PROF                              // phase clocks cost 18 registers: compiled in for experiments only
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-  const bool prof = g.clk != nullptr && blockIdx.x == 0 && tid == 0;
-#define PH(i) do { if (prof) { const long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
-#else
-  constexpr bool prof = false;
-  long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-#define PH(i) do { } while (0)
-#endif
-  for (int s = p; s < n - 1; s += g.P) {
-    int k = 0, r0 = s + 1;
-    cplx taup = zero;                                // tau of the previous step (carried block pending)
-    while (true) {
-      const int ln = min(b, n - r0);
-      if (prof) tlast = clock64();
-      if (k > 0 && ln <= 1) {
-        // nothing to annihilate: flush the carried block (ln rows x b columns) with its pending update
-        for (int idx = tid; idx < ln * b; idx += CT) {
-          const int i = idx % ln, j = idx / ln;
-          cplx a = Bc[(size_t)j * ldb + i];
-          cfms(a, cmul(taup, us[i]), cconj(vp[j]));
-          stg2(AB + (size_t)(r0 - b + j) * LD + (b + i - j), a);
-        }
-        for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = zero;
-        break;
-      }
-      // wait until sweep s-1 is three steps ahead (or finished)
-      if (s > 0) {
-        if (tid == 0) {
-          const int need = k + 3;
-          int spins = 0;                               // bounded: a lost neighbour ends in an error code, not a hang
-          while (ld_acquire(prog + s - 1) < need) {
-            __nanosleep(32);
-            if (++spins > (1 << 24)) { atomicExch(g.status + 2, 1); break; }
-          }
-        }
-        __syncthreads();
-      }
-      PH(0);
-      // ---- prefetch the diagonal block (lower triangle, folded enumeration) into registers; it is
-      //      consumed after the carried block has been flushed out of shared memory
-      cplx dreg[DU];
-#pragma unroll
-      for (int u = 0; u < DU; ++u) {
-        int i, j;
-        dreg[u] = tri_slot(tid + u * CT, ln, i, j) ? ldg2(AB + (size_t)(r0 + j) * LD + (i - j)) : zero;
-      }
-      // ---- A. the column to annihilate
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) xs[i] = ldg2(AB + (size_t)s * LD + 1 + i);
-      } else {
-        for (int i = tid; i < ln; i += CT) {
-          const cplx t = cmul(taup, us[i]);
-          tu[i] = t;
-          xs[i] = csub(Bc[i], t);                       // vp[0] = 1
-        }
-      }
-      __syncthreads();
-      // ---- B. reflector
-      cplx tau; double beta;
-      larfg_block(xs, vs, ln, red, tau, beta);
-      PH(1);
-      for (int i = tid; i < ln; i += CT) V[(size_t)s * n + r0 + i] = vs[i];
-      if (tid == 0) tau2[(size_t)s * g.KT + k] = tau;
-      if (k == 0) {
-        for (int i = tid; i < ln; i += CT) stg2(AB + (size_t)s * LD + 1 + i, (i == 0) ? make_double2(beta, 0.0) : zero);
-      } else {
-        // ---- C. carried block: pending right-application of (vp, taup) and left-application of H^H
-        //   new[i,j] = Bc[i,j] - tu[i] conj(vp[j]) - v[i] conj(tau) z[j],
-        //   z[j] = sum_i conj(v[i]) Bc[i,j] - conj(vp[j]) (v^H tu)
-        cplx c = zero;
-        for (int i = tid; i < ln; i += CT) cfmac(c, vs[i], tu[i]);
-        // column sums: thread = (column, part of the rows)
-        if (mv_part < nparts) {
-          cplx acc = zero;
-          if (mv_row < b) {
-            const int i0 = (int)((long long)ln * mv_part / nparts), i1 = (int)((long long)ln * (mv_part + 1) / nparts);
-            const cplx* col = Bc + (size_t)mv_row * ldb;
-            for (int i = i0; i < i1; ++i) cfmac(acc, vs[i], col[i]);
-          }
-          part[mv_part * PS + mv_row] = acc;
-        }
-        c = block_sum(c, red);                         // (its barriers also publish part[])
-        const cplx ctau = cconj(tau);
-        for (int j = tid; j < b; j += CT) {
-          cplx z = part[j];
-          for (int q = 1; q < nparts; ++q) z = cadd(z, part[q * PS + j]);
-          cfms(z, c, cconj(vp[j]));
-          wc[j] = cmul(ctau, z);
-        }
-        __syncthreads();
-        const int cb = r0 - b;                        // first column of the carried block
-        {
-          int i = tid % ln, j = tid / ln;
-          const int di = CT % ln, dj = CT / ln;
-          while (j < b) {
-            cplx o;
-            if (j == 0) {
-              o = (i == 0) ? make_double2(beta, 0.0) : zero;
-            } else {
-              o = Bc[(size_t)j * ldb + i];
-              cfms(o, tu[i], cconj(vp[j]));
-              cfms(o, vs[i], wc[j]);
-            }
-            stg2(AB + (size_t)(cb + j) * LD + (b - j) + i, o);
-            i += di; j += dj;
-            if (i >= ln) { i -= ln; ++j; }
-          }
-        }
-        __syncthreads();                              // Bc is reused below
-      }
-      PH(2);
-      // ---- D. diagonal block (rows / columns r0 .. r0+ln-1, lower triangle): A <- H^H A H
-      {
-#pragma unroll
-        for (int u = 0; u < DU; ++u) {
-          int i, j;
-          if (tri_slot(tid + u * CT, ln, i, j)) Bc[(size_t)j * ldb + i] = dreg[u];
-        }
-      }
-      // ---- prefetch the next block (rows r1 .. r1+l2-1, columns r0 .. r0+ln-1) into registers
-      const int r1 = r0 + ln;
-      const int l2 = (r1 < n) ? min(b, n - r1) : 0;
-      cplx ereg[EU];
-      {
-        const int tot = l2 * ln;
-        int i = (l2 > 0) ? tid % l2 : 0, j = (l2 > 0) ? tid / l2 : 0;
-        const int di = (l2 > 0) ? CT % l2 : 0, dj = (l2 > 0) ? CT / l2 : 0;
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-          const bool ok = tid + u * CT < tot;
-          ereg[u] = ok ? ldg2(AB + (size_t)(r0 + j) * LD + (ln - j) + i) : zero;
-          i += di; j += dj;
-          if (l2 > 0 && i >= l2) { i -= l2; ++j; }
-        }
-      }
-      __syncthreads();
-      PH(3);
-      {
-        // x = tau D v with D Hermitian, lower triangle stored
-        if (mv_part < nparts) {
-          cplx acc = zero;
-          if (mv_row < ln) {
-            const int i = mv_row;
-            const int j0 = (int)((long long)ln * mv_part / nparts), j1 = (int)((long long)ln * (mv_part + 1) / nparts);
-            for (int j = j0; j < j1; ++j) {
-              const bool low = i >= j;
-              cplx a = Bc[low ? (size_t)j * ldb + i : (size_t)i * ldb + j];
-              if (!low) a.y = -a.y;
-              if (i == j) a.y = 0.0;
-              cfma(acc, a, vs[j]);
-            }
-          }
-          part[mv_part * PS + mv_row] = acc;
-        }
-        __syncthreads();
-        cplx dot = zero;
-        for (int i = tid; i < ln; i += CT) {
-          cplx wv = part[i];
-          for (int q = 1; q < nparts; ++q) wv = cadd(wv, part[q * PS + i]);
-          wv = cmul(tau, wv);                           // x = tau A v
-          xs[i] = wv;
-          cfmac(dot, wv, vs[i]);                        // x^H v
-        }
-        dot = block_sum(dot, red);
-        cplx alpha = cmul(tau, dot);
-        alpha.x *= -0.5; alpha.y *= -0.5;
-        for (int i = tid; i < ln; i += CT) { cplx wv = xs[i]; cfma(wv, alpha, vs[i]); xs[i] = wv; }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < DU; ++u) {
-          int i, j;
-          if (tri_slot(tid + u * CT, ln, i, j)) {
-            cplx a = Bc[(size_t)j * ldb + i];
-            cfms(a, vs[i], cconj(xs[j]));
-            cfms(a, xs[i], cconj(vs[j]));
-            if (i == j) a.y = 0.0;
-            stg2(AB + (size_t)(r0 + j) * LD + (i - j), a);
-          }
-        }
-      }
-      // ---- E. next block: into shared memory, u = Bn v (the update itself is deferred to the next step)
-      if (l2 == 0) break;
-      __syncthreads();                                // the products above read Bc
-      PH(4);
-      {
-        const int tot = l2 * ln;
-        int i = tid % l2, j = tid / l2;
-        const int di = CT % l2, dj = CT / l2;
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-          if (tid + u * CT < tot) Bc[(size_t)j * ldb + i] = ereg[u];
-          i += di; j += dj;
-          if (i >= l2) { i -= l2; ++j; }
-        }
-        __syncthreads();
-        PH(5);
-        if (mv_part < nparts) {
-          cplx acc = zero;
-          if (mv_row < l2) {
-            const int j0 = (int)((long long)ln * mv_part / nparts), j1 = (int)((long long)ln * (mv_part + 1) / nparts);
-            for (int j = j0; j < j1; ++j) cfma(acc, Bc[(size_t)j * ldb + mv_row], vs[j]);
-          }
-          part[mv_part * PS + mv_row] = acc;
-        }
-        __syncthreads();
-        for (int i = tid; i < l2; i += CT) {
-          cplx u = part[i];
-          for (int q = 1; q < nparts; ++q) u = cadd(u, part[q * PS + i]);
-          us[i] = u;
-        }
-        for (int i = tid; i < ln; i += CT) vp[i] = vs[i];
-        taup = tau;
-      }
-      // ---- F. publish
-      __syncthreads();
-      PH(6);
-      if (tid == 0) { __threadfence(); st_release(prog + s, k + 1); }
-      PH(7);
-      r0 = r1;
-      ++k;
-    }
-    __syncthreads();
-    if (tid == 0) { __threadfence(); st_release(prog + s, 1 << 30); }
-  }
-  if (prof) for (int i = 0; i < 8; ++i) g.clk[i] = tph[i];
-#undef PH
-}
-
 // ---- TMA chase kernel for a compile-time half-bandwidth ----------------------------------------------------
-// Same algorithm and data flow as chase_kernel.  The b x b blocks are covered by a TR x TC thread grid with an
+// The b x b blocks are covered by a TR x TC thread grid with an
 // RB x CB sub-block per thread, so every offset is a compile-time constant off one per-thread base and the
 // products run on register operands.  The two b x b block transfers of a step go through the TMA engine instead
 // of the load/store units, as tensor copies over a 3-D tensor map of the skewed band storage (rows beyond the
@@ -1175,14 +867,11 @@ int dw_band_setup(Handle* h, const std::vector<int>& nn, const std::vector<int>&
       if (3 * cand <= n) bw = cand;
       break;
     }
-  // Default wherever a compile-time TMA chase kernel exists for this bandwidth (faster than the dense route at
-  // every size measured, 12 <= L <= 24); DWHMC_BAND=0 forces the dense route, DWHMC_BAND=1 the band route (with
-  // the generic chase kernel if need be).
+  // Default wherever the chase kernels have an instance for this bandwidth (faster than the dense route at every
+  // size measured, 6 <= L <= 24); DWHMC_BAND=0 forces the dense route.
   int want = dw_band_has_tma_kernel(bw) ? 1 : 0;
-  if (const char* e = getenv("DWHMC_BAND")) want = atoi(e);
-  const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
-  // the chase kernel keeps 20 block elements per thread in registers: b^2 <= 20 * 512
-  if (!want || 3 * bw > n || bw > 32 * RQ || (size_t)bw * bw > (size_t)EU * CT || smem > 225 * 1024) return DWHMC_OK;   // dense route
+  if (const char* e = getenv("DWHMC_BAND")) want = want && atoi(e);
+  if (!want || 3 * bw > n) return DWHMC_OK;   // dense route
   // reflectors per block of the back-transformation (band_apply.cu): 32, block height b + 31 <= 136 rows
   if (bw + DW_APPLY_G - 1 > DW_APPLY_ROWS) return DWHMC_OK;                                // dense route
   const int g = DW_APPLY_G;
@@ -1351,9 +1040,6 @@ int dw_band_chase(Handle* h, Mask mask) {
   DW_CUDA(h, cudaMemsetAsync(h->band_prog, 0, sizeof(int) * ((size_t)n + 1) * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_tau, 0, sizeof(cplx) * (size_t)n * h->band_KT * B, h->stream));
   DW_CUDA(h, cudaMemsetAsync(h->band_bbox, 0, sizeof(cplx) * 2 * (size_t)h->band_KT * B, h->stream));
-  // DWHMC_BAND_GENERIC=1: the generic chase kernel (any half-bandwidth <= 101, load/store units instead of TMA) -- the
-  // one fallback of the band route, also used for widths without a compile-time kernel when DWHMC_BAND=1 forces the route
-  static const bool generic = getenv("DWHMC_BAND_GENERIC") != nullptr;
   // Default wherever it has an instance: the position-owning kernel of band_systolic.cu (one chain finishes in n step
   // times instead of 2 n, and the blocks never leave the SM): at L = 24 10.0 instead of 30.5 ms for up to 12 chains and
   // 30.2 instead of 46 ms for 64; L = 20: 15.8 against 18.6 ms for 64 chains, L = 16: 7.0 against 8.3.
@@ -1361,29 +1047,17 @@ int dw_band_chase(Handle* h, Mask mask) {
   static const char* which = getenv("DWHMC_CHASE");
   bool use_sys = dw_band_has_systolic_kernel(bw);
   if (which && which[0] == 's' && which[1] == 'w') use_sys = false;
-  if (!generic && use_sys) DW_TRY(dw_band_chase_systolic(h, mask));
-  else if (!generic && bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
-  else if (!generic && bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
-  else if (!generic && bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
-  else if (!generic && bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));
-  else if (!generic && bw == 60) DW_TRY((chase_tma_dispatch<60, 15, 20, 4, 3>(h, mask)));
-  else if (!generic && bw == 52) DW_TRY((chase_tma_dispatch<52, 13, 26, 4, 2>(h, mask)));
-  else if (!generic && bw == 44) DW_TRY((chase_tma_dispatch<44, 22, 11, 2, 4>(h, mask)));
-  else if (!generic && bw == 36) DW_TRY((chase_tma_dispatch<36, 18, 18, 2, 2>(h, mask)));
-  else if (!generic && bw == 28) DW_TRY((chase_tma_dispatch<28, 14, 14, 2, 2>(h, mask)));
-  else {
-    const size_t smem = sizeof(cplx) * chase_smem_elems(bw);
-    static bool attr_set[64] = {false};
-    if (!attr_set[h->device & 63]) {
-      DW_CUDA(h, cudaFuncSetAttribute(chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      attr_set[h->device & 63] = true;
-    }
-    DW_TRY(chase_launch_loop(h, mask, (const void*)chase_kernel, CT, smem, false, [&](ChaseArgs& a, int ctas) -> int {
-      void* args[] = {&a};
-      DW_CUDA(h, cudaLaunchCooperativeKernel((void*)chase_kernel, dim3(ctas), dim3(CT), args, smem, h->stream));
-      return DWHMC_OK;
-    }));
-  }
+  if (use_sys) DW_TRY(dw_band_chase_systolic(h, mask));
+  else if (bw == 100) DW_TRY((chase_tma_dispatch<100, 25, 19, 4, 6>(h, mask)));
+  else if (bw == 84) DW_TRY((chase_tma_dispatch<84, 21, 21, 4, 4>(h, mask)));
+  else if (bw == 76) DW_TRY((chase_tma_dispatch<76, 19, 19, 4, 4>(h, mask)));
+  else if (bw == 68) DW_TRY((chase_tma_dispatch<68, 17, 17, 4, 4>(h, mask)));
+  else if (bw == 60) DW_TRY((chase_tma_dispatch<60, 15, 20, 4, 3>(h, mask)));
+  else if (bw == 52) DW_TRY((chase_tma_dispatch<52, 13, 26, 4, 2>(h, mask)));
+  else if (bw == 44) DW_TRY((chase_tma_dispatch<44, 22, 11, 2, 4>(h, mask)));
+  else if (bw == 36) DW_TRY((chase_tma_dispatch<36, 18, 18, 2, 2>(h, mask)));
+  else if (bw == 28) DW_TRY((chase_tma_dispatch<28, 14, 14, 2, 2>(h, mask)));
+  else { h->err = "dw_band_chase: no kernel for this half-bandwidth"; return DWHMC_E_BADARG; }
   dim3 grid((n + 255) / 256, B);
   band_de_kernel<<<grid, 256, 0, h->stream>>>(h->A, h->d, h->e, n, h->band_LD, mask);
   DW_LAUNCH_CHECK(h);

@@ -753,14 +753,12 @@ def test_default_route_is_band_where_a_chase_kernel_exists(dw):
 
 
 CHASE_SWITCH_SHAPES = {
-    # the generic kernel (load/store units): L = 8 (b = 36) and a rectangle whose half-bandwidth is rounded up (24 -> 28)
-    "DWHMC_BAND_GENERIC=1": (["8", "3"], ["5x13", "2"]),
     # the position-owning kernel (the default) with short epochs: every position changes CTAs every 16 / 37 sweeps
     # through the band storage, at L = 8 with more tasks than CTAs, at L = 24, and on a rectangle
     "DWHMC_CHASE_Q=16": (["8", "150"], ["24", "3"], ["5x13", "2"]),
     "DWHMC_CHASE_Q=37": (["16", "40"], ["6x10", "3"]),
     # the sweep-owning kernel (band.cu), the band route's second kernel
-    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"], ["8", "150"], ["16", "64"]),
+    "DWHMC_CHASE=sweep": (["24", "2"], ["12", "5"], ["6x10", "3"], ["8", "150"], ["16", "64"], ["5x13", "2"]),
 }
 
 
@@ -769,7 +767,8 @@ def test_chase_fallback_kernels(switch):
     """The bulge-chase kernels behind their (process-wide, read-once) switches against LAPACK, each in a process of its
     own: eigenvalues, residual and unitarity of two chains per shape.  The default is the position-owning kernel
     (band_systolic.cu; every other GPU test runs it, with one epoch for small batches and epochs of 5 b / 4 sweeps for
-    large ones); here: short epochs, the sweep-owning kernel (band.cu) and the generic kernel."""
+    large ones); here: short epochs and the sweep-owning kernel (band.cu), the band route's one fallback, incl. a
+    rectangle whose half-bandwidth is rounded up (5 x 13: 24 -> 28)."""
     import re
     import subprocess
     import sys
