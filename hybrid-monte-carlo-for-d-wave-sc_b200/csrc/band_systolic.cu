@@ -852,11 +852,11 @@ bool dw_band_has_systolic_kernel(int bw) {
 int dw_band_chase_systolic(Handle* h, Mask mask) {
   switch (h->band_b) {
     case 100: return sys_dispatch<100, 50, 7, 2, 15>(h, mask);   // 2 x 15 elements per thread: the row operands of an update fit next to the block
-    case 84: return sys_dispatch<84, 21, 16, 4, 6>(h, mask);
-    case 76: return sys_dispatch<76, 19, 19, 4, 4>(h, mask);
-    case 68: return sys_dispatch<68, 17, 17, 4, 4>(h, mask);
-    case 60: return sys_dispatch<60, 15, 20, 4, 3>(h, mask);
-    case 52: return sys_dispatch<52, 13, 26, 4, 2>(h, mask);
+    case 84: return sys_dispatch<84, 42, 8, 2, 11>(h, mask);     // (two rows per thread everywhere: 8-10 % ahead of 4 x 4 ... 4 x 6 blocks)
+    case 76: return sys_dispatch<76, 38, 10, 2, 8>(h, mask);
+    case 68: return sys_dispatch<68, 34, 10, 2, 7>(h, mask);
+    case 60: return sys_dispatch<60, 30, 10, 2, 6>(h, mask);
+    case 52: return sys_dispatch<52, 26, 13, 2, 4>(h, mask);
     case 44: return sys_dispatch<44, 22, 11, 2, 4>(h, mask);
     case 36: return sys_dispatch<36, 18, 18, 2, 2>(h, mask);
     case 28: return sys_dispatch<28, 14, 14, 2, 2>(h, mask);
