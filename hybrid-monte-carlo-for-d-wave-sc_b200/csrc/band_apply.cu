@@ -84,31 +84,33 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       Vs[r * (TG + 1) + c] = ok ? V[(size_t)(s0 + c) * n + rlo + rr] : zero;
     }
   };
-  // Gram matrix, accumulated over row chunks
-  constexpr int PAIRS = (TG * TG + 255) / 256;
-  cplx acc[PAIRS];
-#pragma unroll
-  for (int q = 0; q < PAIRS; ++q) acc[q] = zero;
+  // Gram matrix, accumulated over row chunks; only its upper triangle G[c1, c2] = v_c1^H v_c2, c1 < c2, is read below.
+  // Thread (ti, tj) = (tid mod 16, tid / 16) owns the pair (ti, tj + 16) and, if ti <= tj, the pairs (ti, tj) and
+  // (ti + 16, tj + 16): four loads (two of consecutive lanes, two broadcast) for up to three products per row
+  // (g = 32 = TG: dw_band_setup).
+  const int ti = tid & 15, tj = tid >> 4;
+  const bool upper = ti <= tj;
+  cplx gA = zero, gB = zero, gC = zero;
   for (int rc = 0; rc < rows; rc += 32) {
     __syncthreads();
     load_chunk(rc);
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < PAIRS; ++q) {
-      const int pidx = tid + 256 * q;
-      const int c1 = pidx % g, c2 = pidx / g;
-      if (c2 < gg && c1 < gg) {
-        cplx a = acc[q];
-        for (int r = 0; r < 32; ++r) cfmac(a, Vs[r * (TG + 1) + c1], Vs[r * (TG + 1) + c2]);
-        acc[q] = a;
+    for (int r = 0; r < 32; ++r) {
+      const cplx a0 = Vs[r * (TG + 1) + ti], b1 = Vs[r * (TG + 1) + tj + 16];
+      cfmac(gA, a0, b1);
+      if (upper) {
+        cfmac(gB, a0, Vs[r * (TG + 1) + tj]);
+        cfmac(gC, Vs[r * (TG + 1) + ti + 16], b1);
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < PAIRS; ++q) {
-    const int pidx = tid + 256 * q;
-    const int c1 = pidx % g, c2 = pidx / g;
-    if (c2 < g && c1 < g) G[c2 * g + c1] = (c2 < gg && c1 < gg) ? acc[q] : zero;   // G[c1, c2] = v_c1^H v_c2
+  for (int idx = tid; idx < g * g; idx += 256) G[idx] = zero;
+  __syncthreads();
+  {
+    const bool okA = ti < gg && tj + 16 < gg, okB = upper && tj < gg, okC = upper && tj + 16 < gg;
+    if (okA) G[(tj + 16) * g + ti] = gA;
+    if (okB) G[tj * g + ti] = gB;
+    if (okC) G[(tj + 16) * g + ti + 16] = gC;
   }
   for (int idx = tid; idx < g * (g + 1); idx += 256) T[idx] = zero;
   __syncthreads();
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
     load_chunk(rc);
     if (tid < TG) for (int c = gg; c < TG; ++c) Vs[tid * (TG + 1) + c] = zero;     // columns of a short last group
     __syncthreads();
+    double* stage = reinterpret_cast<double*>(G);      // [32 rows][33]: the transposed plane goes out row by row (G is dead)
     for (int idx = tid; idx < 32 * A2_G; idx += 256) {
       const int r = idx & 31, m = idx >> 5;
       if (rc + r >= A2_ROWS) continue;
@@ -145,10 +148,15 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
       if (m < gg && rc + r < rows)
         for (int j = 0; j <= m; ++j) cfma(a, Vs[r * (TG + 1) + j], T[j * (g + 1) + m]);     // T upper triangular
       ntx[m * A2_ROWS + rc + r] = make_double2(-a.x, a.x - a.y);
-      nts[(rc + r) * A2_LDT + m] = -a.x - a.y;
+      stage[r * 33 + m] = -a.x - a.y;
       const cplx v = Vs[r * (TG + 1) + m];
       cvx[m * A2_ROWS + rc + r] = make_double2(v.x, -v.y - v.x);
       cvs[m * A2_ROWS + rc + r] = v.x - v.y;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 32 * A2_G; idx += 256) {
+      const int m = idx & 31, r = idx >> 5;
+      if (rc + r < A2_ROWS) nts[(rc + r) * A2_LDT + m] = stage[r * 33 + m];
     }
   }
 }
