@@ -114,19 +114,24 @@ __global__ void __launch_bounds__(256) band_tfactor_kernel(const cplx* __restric
   }
   for (int idx = tid; idx < g * (g + 1); idx += 256) T[idx] = zero;
   __syncthreads();
-  // T[i,i] = tau_i ; T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i] ; thread r owns row r
-  if (tid < g) {
-    const int r = tid;
+  // T[i,i] = tau_i ; T[0:i, i] = -tau_i T[0:i,0:i] G[0:i, i] ; eight lanes share row r (the rows are independent of
+  // each other, so a warp barrier per column is all the synchronisation the recurrence needs)
+  {
+    const int r = tid >> 3, part = tid & 7;
     cplx* Tr = T + r * (g + 1);
     for (int i = 0; i < gg; ++i) {
       const cplx t = tau2[((size_t)ch * n + s0 + i) * KT + k];
-      if (r < i) {
-        cplx s = zero;
-        for (int l = r; l < i; ++l) cfma(s, Tr[l], G[i * g + l]);
-        Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
-      } else if (r == i) {
-        Tr[i] = t;
+      cplx s = zero;
+      if (r < i)
+        for (int l = r + part; l < i; l += 8) cfma(s, Tr[l], G[i * g + l]);
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, 1); s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, 2); s.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, 4); s.y += __shfl_xor_sync(0xffffffffu, s.y, 4);
+      if (part == 0) {
+        if (r < i) Tr[i] = make_double2(-(t.x * s.x - t.y * s.y), -(t.x * s.y + t.y * s.x));
+        else if (r == i) Tr[i] = t;
       }
+      __syncwarp();
     }
   }
   // conj(Vb) and -Vb T as (c, d - c) pairs and c + d planes
