@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
         if (have_corner) hbar_arrive<NC>(BAR_CORNER);
         hbar_sync<NC>(BAR_RW);
-        if (l0) st_release(fl + KT + k, s + 1);
+        if (l0) { __threadfence(); st_release(fl + KT + k, s + 1); }
         if (!have_row) {
           { HW_BEGIN(2) wait_for(fl + KT + (k + 1), s); HW_END() }
           fetch_row();
@@ -328,13 +328,13 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           hbar_arrive<NC>(BAR_CORNER);
         }
         hbar_sync<NC>(BAR_DW);
-        if (l0) st_release(fl + 2 * KT + k, s + 1);
+        if (l0) { __threadfence(); st_release(fl + 2 * KT + k, s + 1); }
         ++r0;
         o = (o + 1 == TB) ? 0 : o + 1;
       }
       hbar_sync<NC>(BAR_SAVE);                         // windows written back (if the position goes on in the next epoch)
       HW_TASK_END();
-      if (l0 && s1 < n - 1 - k * TB) st_release(fl + 3 * KT + k, ep + 1);
+      if (l0 && s1 < n - 1 - k * TB) { __threadfence(); st_release(fl + 3 * KT + k, ep + 1); }
     }
   }
 
@@ -651,17 +651,21 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
       {
         cplx alpha2 = cmul(lds2(scal + 4), red_sum());
         alpha2.x *= -0.5; alpha2.y *= -0.5;
-        for (int p = tid; p < TB; p += NC) { cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w; }
+        for (int p = tid; p < TB; p += NC) {
+          cplx w = ys[p]; cfma(w, alpha2, vs[p]); ys[p] = w;
+          if (p == o) {
+            // the corner message: D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band
+            // storage.  It is formed here, by the thread that has w[0], because D is not stable once the barrier
+            // below has opened: the first warps of the update phase rewrite D[0,0] at once.
+            const cplx c = make_double2(D[o * LDD + o].x - 2.0 * w.x, 0.0);
+            if (k > 0) stg2(g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2) + TB, c);
+            else stg2(AB + (size_t)r0 * LD, c);
+          }
+        }
       }
       csync<NC>();
       PH(11);
-      // ---- P7: corner message out, then the two block updates
-      if (tid == 0) {
-        // D[0,0] after the update (v[0] = 1); position 0: d[s+1], straight into the band storage
-        const cplx c = make_double2(D[o * LDD + o].x - 2.0 * ys[o].x, 0.0);
-        if (k > 0) stg2(g.rowbox + (((size_t)chain * KT + k) * 2 + buf) * (TB + 2) + TB, c);
-        else stg2(AB + (size_t)r0 * LD, c);
-      }
+      // ---- P7: the corner message is on its way; the two block updates
       hbar_arrive<NC>(BAR_DW);
       if (act) {
         // Two independent updates: Bc in registers (pure FP64 work; row operands v, tu held, column operands by broadcast
