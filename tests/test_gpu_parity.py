@@ -721,6 +721,51 @@ def test_two_handles_concurrently(dw):
         cbs[i].close()
 
 
+def test_chase_bitwise_reproducible_beside_another_handle(dw):
+    """The band -> tridiagonal reduction of one handle gives the same bits on every run while a second handle keeps the
+    SMs busy from another host thread.  (Regression: the corner message of the position-owning chase was once read
+    from shared memory after the barrier behind which other warps rewrite it; about 1 run in 100 at this size then
+    had one wrong diagonal entry.  tools/chase_race_check.py is the long version.)"""
+    import threading
+    L, B = 12, 12
+    N = L * L
+
+    def make(seed, nb):
+        cb = dw.ChainBatch(nb, L, L)
+        cb.set_params(1.0, -0.35, -1.08, np.linspace(2, 40, nb), 0.8, 1.0)
+        w = np.zeros((nb, N)); w[:, :7] = 1.0
+        cb.set_disorder(w)
+        r = np.random.default_rng(seed)
+        cb.set_field((r.random((nb, 2, N)) - 0.5 + 1j * (r.random((nb, 2, N)) - 0.5)) * 0.1)
+        cb.init_static_H(); cb.update_H_BdG()
+        return cb
+
+    a = make(1, B)
+    d0, e0 = (x.copy() for x in a.debug_tridiagonalize())
+    b = make(2, 40)
+    b.diagonalize_H_BdG(); b.seed(2)
+    stop = threading.Event()
+
+    def noise():
+        dt = np.full(40, 0.05)
+        while not stop.is_set():
+            b.run_sweeps(1, 3, dt)
+
+    th = threading.Thread(target=noise)
+    th.start()
+    try:
+        bad = 0
+        for _ in range(250):
+            d, e = a.debug_tridiagonalize()
+            bad += not (np.array_equal(d, d0) and np.array_equal(e, e0))
+    finally:
+        stop.set()
+        th.join(timeout=120)
+    assert not th.is_alive(), "the second handle hung"
+    assert bad == 0, f"{bad} of 250 tridiagonalisations differ from the quiet run"
+    a.close(); b.close()
+
+
 def test_dense_route_against_oracle(dw, monkeypatch):
     """The dense eigensolver route (DWHMC_BAND=0: blocked tridiagonalisation + back-transformation; the route of
     lattices whose half-bandwidth exceeds 100, e.g. L = 32, see tests/test_gpu_round2.py for that size) against the
