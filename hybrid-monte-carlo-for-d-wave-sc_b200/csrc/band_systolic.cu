@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
         }
         if (have_corner) hbar_arrive<NC>(BAR_CORNER);
         hbar_sync<NC>(BAR_RW);
-        if (l0) { __threadfence(); st_release(fl + KT + k, s + 1); }
+        if (l0) { st_release(fl + KT + k, s + 1); }
         if (!have_row) {
           { HW_BEGIN(2) wait_for(fl + KT + (k + 1), s); HW_END() }
           fetch_row();
@@ -328,13 +328,13 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           hbar_arrive<NC>(BAR_CORNER);
         }
         hbar_sync<NC>(BAR_DW);
-        if (l0) { __threadfence(); st_release(fl + 2 * KT + k, s + 1); }
+        if (l0) { st_release(fl + 2 * KT + k, s + 1); }
         ++r0;
         o = (o + 1 == TB) ? 0 : o + 1;
       }
       hbar_sync<NC>(BAR_SAVE);                         // windows written back (if the position goes on in the next epoch)
       HW_TASK_END();
-      if (l0 && s1 < n - 1 - k * TB) { __threadfence(); st_release(fl + 3 * KT + k, ep + 1); }
+      if (l0 && s1 < n - 1 - k * TB) { st_release(fl + 3 * KT + k, ep + 1); }
     }
   }
 
