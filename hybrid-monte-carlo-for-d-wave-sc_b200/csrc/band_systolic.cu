@@ -524,24 +524,25 @@ __global__ void __launch_bounds__(sys_nc(TR, TC) + 32, 1) chase_sys_kernel(SysAr
           scale = make_double2(dr * iden, -di * iden);
           betac = make_double2(beta, 0.0);
         }
-        for (int p = tid; p < TB; p += NC) vs[p] = (p == o) ? make_double2(1.0, 0.0) : cmul(xs[p], scale);
-        if (tid == 0) { scal[4] = tau; scal[5] = betac; }   // later phases re-read them (registers are scarce)
-      }
-      csync<NC>();
-      PH(4);
-      {
+        // v, tau and beta leave for the neighbours from the registers they are computed in (they are on the cycle
+        // between neighbouring positions twice per sweep: no barrier and no second pass in front of them)
         cplx* Vcol = g.V + ((size_t)chain * n + s) * n + r0;
         for (int p = tid; p < TB; p += NC) {
+          const cplx v = (p == o) ? make_double2(1.0, 0.0) : cmul(xs[p], scale);
+          vs[p] = v;
           const int lg = p - o + (p < o ? TB : 0);
-          if (r0 + lg < n) stg2(Vcol + lg, flush ? zero : vs[p]);
+          if (r0 + lg < n) stg2(Vcol + lg, flush ? zero : v);
         }
         if (tid == 0) {
-          stg2(g.tau2 + ((size_t)chain * n + s) * KT + k, lds2(scal + 4));
-          if (k == 0) stg2(AB + (size_t)s * LD + 1, lds2(scal + 5));   // e[s]
-          else stg2(g.bbox + ((size_t)chain * KT + k) * 2, lds2(scal + 5));   // beta: position k-1 needs it before anything else
+          scal[4] = tau; scal[5] = betac;                 // later phases re-read them (registers are scarce)
+          stg2(g.tau2 + ((size_t)chain * n + s) * KT + k, tau);
+          if (k == 0) stg2(AB + (size_t)s * LD + 1, betac);   // e[s]
+          else stg2(g.bbox + ((size_t)chain * KT + k) * 2, betac);   // beta: position k-1 needs it before anything else
         }
       }
       hbar_arrive<NC>(BAR_VW);
+      csync<NC>();
+      PH(4);
       // ---- P4a-P6a (positions k > 0): z = v^H Bc, wc = conj(tau) z, and row r0 of the updated Bc -- the row message
       //      position k-1 is waiting for -- ahead of everything that does not feed it
       if (k > 0) {
