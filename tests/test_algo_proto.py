@@ -76,3 +76,24 @@ def test_systolic_chase_prototype_matches_sweep_owning_prototype():
         scale = np.max(np.abs(A))
         assert np.max(np.abs(d0 - d1)) <= 1e-12 * scale and np.max(np.abs(e0 - e1)) <= 1e-12 * scale
         assert np.max(np.abs(V0 - V1)) <= 1e-11 and np.max(np.abs(T0 - T1)) <= 1e-11
+
+
+def test_deferred_update_prototype_matches_systolic_prototype():
+    """tests/algo_proto_deferred.py (the next step for the chase kernel, DESIGN.md section 7: the rank-2 updates of the
+    diagonal window are kept as m pending pairs, the leaving column is refreshed just in time, the pairs are applied as
+    one GEMM-shaped block update every m sweeps) gives the same tridiagonal matrix, reflectors and tau as the
+    step-by-step prototype of the kernel as it is."""
+    import algo_proto_systolic as aps
+    import algo_proto_deferred as apd
+    rng = np.random.default_rng(2)
+    for n, b, m in ((23, 4, 3), (40, 7, 4), (37, 5, 8), (64, 12, 8), (30, 28, 5), (50, 3, 2), (45, 9, 1)):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        A = A + A.conj().T
+        i, j = np.indices((n, n))
+        A[np.abs(i - j) > b] = 0
+        d1, e1, V1, T1 = aps.chase_systolic(A, b)
+        d2, e2, V2, T2, nblock = apd.chase_systolic_deferred(A, b, m)
+        scale = np.max(np.abs(A))
+        assert np.max(np.abs(d1 - d2)) <= 1e-12 * scale and np.max(np.abs(e1 - e2)) <= 1e-12 * scale
+        assert np.max(np.abs(V1 - V2)) <= 1e-11 and np.max(np.abs(T1 - T2)) <= 1e-11
+        assert nblock > 0
